@@ -1,0 +1,175 @@
+/*
+ * raymesh_b200.h — C ABI of the B200-native ray/mesh intersector (libtriro_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of lcp29/trimesh-ray-optix ("Triro").
+ * Every entry point replaces one piece of the reference's native interface
+ * (pybind11 module `triro`, triro/backend/binding.cpp:31-59).  Citations below are
+ * relative to the reference tree.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types in any signature;
+ *   - every function returns 0 on success, a negative rt_status on failure; the
+ *     message is available through rt_last_error() (thread-local).  Nothing here
+ *     throws or calls exit() (the reference exits the interpreter on OptiX errors,
+ *     triro/backend/optix8.h:41-49);
+ *   - all pointers except where noted are DEVICE pointers on the current CUDA device;
+ *     memory is owned by the caller (the Python host allocates it with torch);
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *     all work is asynchronous on that stream, there is no hidden synchronisation;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails.
+ */
+#ifndef RAYMESH_B200_H
+#define RAYMESH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+/* reference: LaunchParams.h:8-9 */
+#define RT_MAX_ANYHIT_SIZE 8
+#define RT_MAX_SIZE_LENGTH 4
+/* reference: tmin = 0, tmax = 1e7 on every optixTrace, shaders.cu:86,112,163,191,238 */
+#define RT_TMAX_DEFAULT 1.0e7f
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, misalignment) */
+    RT_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    RT_ERR_SIZE = -3,      /* caller buffer too small */
+    RT_ERR_BLOB = -4,      /* not a BVH blob of this ABI version */
+    RT_ERR_DEPTH = -5      /* BVH deeper than the traversal stack (degenerate mesh) */
+} rt_status;
+
+/*
+ * Strided ray batch.  Mirrors `RayInput` (LaunchParams.h:11-28) as filled by
+ * `fillArray` (ray.cpp:151-159): the tensor shape [*b, 3] is right-aligned into
+ * 4 slots; strides are in ELEMENTS (floats), any value including 0 (broadcast) and
+ * negative.  Missing leading dimensions have shape 1 / stride 0.  As in the
+ * reference (ray.cpp:177-179) the shape of `origins` is used for both tensors.
+ * Ray r (row-major over shape[0..2]) reads component k of its origin at
+ *   origins[i0*o_stride[0] + i1*o_stride[1] + i2*o_stride[2] + k*o_stride[3]].
+ * (shaders.cu:27-63; the reference's 32-bit `idx*3` overflow is not reproduced:
+ * indices are 64-bit.)
+ */
+typedef struct rt_ray_desc {
+    int64_t nray;
+    int64_t shape[RT_MAX_SIZE_LENGTH];
+    const float* origins;
+    int64_t o_stride[RT_MAX_SIZE_LENGTH];
+    const float* directions;
+    int64_t d_stride[RT_MAX_SIZE_LENGTH];
+} rt_ray_desc;
+
+/* Host-readable copy of the blob header (first RT_BLOB_HEADER_BYTES of a blob). */
+#define RT_BLOB_HEADER_BYTES 256
+#define RT_BLOB_MAGIC 0x38485642u /* "BVH8" */
+typedef struct rt_blob_header {
+    uint32_t magic;
+    uint32_t abi_version;
+    uint32_t n_tris;
+    uint32_t n_nodes;       /* 80-byte BVH8 nodes in use */
+    uint32_t depth;         /* wide-tree levels (traversal stack bound) */
+    uint32_t n_nodes_cap;
+    uint64_t tris_offset;   /* byte offset of the 48-byte triangle records */
+    uint64_t nodes_offset;  /* byte offset of the node array */
+    uint64_t used_bytes;    /* prefix of the blob that must travel (NCCL broadcast / save) */
+    float aabb_lo[3];
+    float aabb_hi[3];
+    uint32_t reserved[44];
+} rt_blob_header;
+
+/* Size of the scratch buffer every trace call needs (zeroed by the call itself). */
+#define RT_TRACE_SCRATCH_BYTES 256
+
+const char* rt_last_error(void);
+int rt_abi_version(void);
+/* number of SMs of the current device (0 when there is no device) */
+int rt_device_sm_count(void);
+
+/* ---- BVH build: replaces OptixAccelStructureWrapperCPP::buildAccelStructure
+ *      (ray.cpp:27-100) = optixAccelComputeMemoryUsage + optixAccelBuild + optixAccelCompact.
+ *      Morton codes -> onesweep radix sort -> Karras LBVH -> refit -> 8-wide quantised nodes. */
+int rt_bvh_sizes(int64_t n_verts, int64_t n_faces, size_t* workspace_bytes, size_t* blob_bytes);
+int rt_bvh_build(const float* vertices, int64_t n_verts,   /* [n_verts,3] f32 contiguous */
+                 const int32_t* faces, int64_t n_faces,    /* [n_faces,3] i32 contiguous */
+                 void* workspace, size_t workspace_bytes,
+                 void* blob, size_t blob_bytes, void* stream);
+/* ---- Radix sort exposed for testing (the builder's onesweep sort, 64-bit key + 32-bit value). */
+int rt_sort_sizes(int64_t n, size_t* workspace_bytes);
+int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, int64_t n, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- Trace entry points.  `scratch` = RT_TRACE_SCRATCH_BYTES device bytes private to the call. */
+/* replaces intersectsAny (ray.cpp:161-189; programs shaders.cu:67-89): hit[r] = 1 iff some triangle
+ * is hit with 0 < t < 1e7. */
+int rt_trace_any(const void* blob, const rt_ray_desc* rays, uint8_t* hit, void* scratch, void* stream);
+/* replaces intersectsFirst (ray.cpp:191-219; shaders.cu:93-116): nearest-hit triangle index or -1. */
+int rt_trace_first(const void* blob, const rt_ray_desc* rays, int32_t* tri_idx, void* scratch, void* stream);
+/* replaces intersectsClosest (ray.cpp:231-289; shaders.cu:120-172).  Outputs dense in ray order:
+ * hit u8, front u8, tri i32 (-1 on miss), loc f32x3 (0 on miss), uv f32x2 = (w0, w1) (0 on miss). */
+int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8_t* hit, uint8_t* front,
+                     int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
+/* replaces intersectsCount (ray.cpp:291-322; shaders.cu:176-194): exact number of triangles hit. */
+int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream);
+
+/* ---- Stream compaction: replaces the boolean-mask indexing of ray_optix.py:142-144 / :219-223.
+ *      Step 1 scans the hit mask (decoupled look-back), writing one exclusive prefix per
+ *      RT_COMPACT_TILE rays and the total; the host reads `total` to size the outputs
+ *      (the only sync the reference API makes unavoidable); step 2 scatters. */
+#define RT_COMPACT_TILE 2048
+int rt_compact_sizes(int64_t nray, size_t* workspace_bytes);
+int rt_compact_scan(const uint8_t* hit, int64_t nray, void* workspace, size_t workspace_bytes,
+                    int64_t* total_dev, void* stream);
+int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* workspace,
+                       const uint8_t* front, const int32_t* tri_idx, const float* loc, const float* uv,
+                       uint8_t* front_out, int32_t* ray_idx_out, int32_t* tri_idx_out, float* loc_out,
+                       float* uv_out, void* stream);
+
+/* ---- All hits: replaces intersectsLocation (ray.cpp:324-378; shaders.cu:196-246), i.e. the
+ *      reference's count pass + clamp/cumsum (ray.cpp:333-342) + second traversal, in ONE traversal:
+ *      step 1 traces once, storing up to max_hits (<= RT_MAX_ANYHIT_SIZE) hits per ray into
+ *      `staging` (nray * max_hits * 16 bytes: tri, x, y, z) and the clamped count per ray, then
+ *      scans the counts; step 2 packs them by ray. */
+int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_bytes, size_t* workspace_bytes);
+int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, int32_t* count_clamped,
+                     void* staging, void* workspace, size_t workspace_bytes, int64_t* total_dev,
+                     void* scratch, void* stream);
+int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
+                       const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
+                       void* stream);
+
+/* ---- contains_points core: replaces the two intersectsCount launches + ~15 torch kernels of
+ *      ray_optix.py:236-267.  For each point traces +dir and -dir exhaustively and writes
+ *        contain[i] = inside_aabb & odd(+) & odd(-)
+ *        broken[i]  = !(odd(+) & odd(-)) & (count(+)==0 | count(-)==0)
+ *      flags_dev[0] = any(inside_aabb), flags_dev[1] = any(broken).  `points` describes
+ *      the point batch through the origins fields of rt_ray_desc (directions ignored). */
+int rt_contains_parity(const void* blob, const rt_ray_desc* points, const float dir[3],
+                       const float aabb_lo[3], const float aabb_hi[3], uint8_t* contain,
+                       uint8_t* broken, int32_t* flags_dev, void* scratch, void* stream);
+
+/* ---- Instrumented traversal (same code path, counters compiled in): feeds the
+ *      bytes-per-ray figure of the roofline.  mode: 0 closest, 1 any, 2 count.
+ *      counters_dev[0] = BVH8 nodes fetched, [1] = triangles fetched, [2] = rays, [3] = hits. */
+int rt_trace_stats(const void* blob, const rt_ray_desc* rays, int mode, uint64_t* counters_dev,
+                   void* scratch, void* stream);
+
+/* ---- Host-buffer entry point (end-to-end path): rays and results live in (pinned) HOST memory.
+ *      Copies ray chunks H2D, traces and copies results D2H on internal streams, overlapping
+ *      the three; `dev_work` is caller-provided device memory of rt_host_closest_sizes() bytes.
+ *      Synchronous: returns when the results are in the host buffers. */
+int rt_host_closest_sizes(int64_t nray, size_t* dev_work_bytes);
+int rt_host_trace_closest(const void* blob, int64_t nray, const float* h_origins /* [nray,3] or [1,3] */,
+                          int origins_broadcast, const float* h_directions /* [nray,3] */,
+                          uint8_t* h_hit, uint8_t* h_front, int32_t* h_tri_idx, float* h_loc, float* h_uv,
+                          void* dev_work, size_t dev_work_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYMESH_B200_H */

@@ -1,0 +1,264 @@
+// hostsim.cpp — TEST INFRASTRUCTURE ONLY.  Host-side single-threaded stepping of the product's
+// per-element device functions (rt_core.cuh / rt_traverse.cuh / rt_build_core.cuh, which are
+// __host__ __device__) so that the builder and traversal LOGIC can be checked against the oracle
+// in the CPU-only test tier, and so that a blob produced on the GPU can be validated structurally
+// (hs_check_blob).  It is compiled into tests/hostsim/libhostsim.so by tests; it is never linked
+// into libtriro_b200.so and nothing under trimesh-ray-optix_b200/ refers to it: the product has
+// no CPU path.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -mfma -shared -fPIC hostsim.cpp -o libhostsim.so
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "../../include/raymesh_b200.h"
+#include "../../trimesh-ray-optix_b200/csrc/rt_build_core.cuh"
+#include "../../trimesh-ray-optix_b200/csrc/rt_traverse.cuh"
+
+using namespace rt;
+
+namespace {
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+struct Layout { size_t tris_offset, nodes_offset, total; uint32_t node_cap; };
+Layout layout(int64_t n) {
+    Layout l;
+    l.tris_offset = RT_BLOB_HEADER_BYTES;
+    l.nodes_offset = align_up(l.tris_offset + (size_t)n * 48u, 256);
+    l.node_cap = (uint32_t)(n / 3 + 2);
+    l.total = l.nodes_offset + (size_t)l.node_cap * 80u;
+    return l;
+}
+struct VecStack {
+    uint32_t x[kMaxDepth], y[kMaxDepth];
+    int max_sp = 0;
+    void push(int sp, uint32_t a, uint32_t b) { x[sp] = a; y[sp] = b; if (sp + 1 > max_sp) max_sp = sp + 1; }
+    void pop(int sp, uint32_t& a, uint32_t& b) { a = x[sp]; b = y[sp]; }
+};
+void tri_verts(const float* verts, int64_t nv, const int32_t* faces, int64_t prim, float v[9]) {
+    for (int c = 0; c < 3; ++c) {
+        const int32_t i = clamp_index(faces[3 * prim + c], nv);
+        v[3 * c] = verts[3 * (size_t)i]; v[3 * c + 1] = verts[3 * (size_t)i + 1]; v[3 * c + 2] = verts[3 * (size_t)i + 2];
+    }
+}
+}  // namespace
+
+extern "C" size_t hs_blob_bytes(int64_t n_faces) { return layout(n_faces).total; }
+
+// Same pipeline as rt_bvh_build, one element at a time.
+extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, int64_t n, uint8_t* blob, size_t blob_bytes) {
+    const Layout lay = layout(n);
+    if (blob_bytes < lay.total) return -3;
+    memset(blob, 0, lay.total);
+    rt_blob_header h;
+    memset(&h, 0, sizeof(h));
+    h.magic = RT_BLOB_MAGIC; h.abi_version = RT_ABI_VERSION; h.n_tris = (uint32_t)n; h.n_nodes_cap = lay.node_cap;
+    h.tris_offset = lay.tris_offset; h.nodes_offset = lay.nodes_offset;
+    if (n == 0) {
+        Node8 nd; memset(&nd, 0, sizeof(nd)); nd.ex = nd.ey = nd.ez = 1;
+        for (int s = 0; s < 8; ++s) nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
+        memcpy(blob + lay.nodes_offset, &nd, 80);
+        h.n_nodes = 1; h.depth = 1; h.used_bytes = lay.nodes_offset + 80;
+        memcpy(blob, &h, sizeof(h));
+        return 0;
+    }
+    // scene bounds + Morton codes
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    std::vector<BBox> tb((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        float v[9]; tri_verts(verts, nv, faces, i, v);
+        tb[i] = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+        lo[0] = fminf(lo[0], tb[i].lx); lo[1] = fminf(lo[1], tb[i].ly); lo[2] = fminf(lo[2], tb[i].lz);
+        hi[0] = fmaxf(hi[0], tb[i].hx); hi[1] = fmaxf(hi[1], tb[i].hy); hi[2] = fmaxf(hi[2], tb[i].hz);
+    }
+    float inv[3];
+    for (int a = 0; a < 3; ++a) { const float e = hi[a] - lo[a]; inv[a] = e > 0.0f ? 1.0f / e : 0.0f; }
+    std::vector<uint64_t> keys((size_t)n);
+    std::vector<uint32_t> vals((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        keys[i] = morton63(0.5f * (tb[i].lx + tb[i].hx), 0.5f * (tb[i].ly + tb[i].hy), 0.5f * (tb[i].lz + tb[i].hz), lo, inv);
+        vals[i] = (uint32_t)i;
+    }
+    std::stable_sort(vals.begin(), vals.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> skeys((size_t)n);
+    for (int64_t i = 0; i < n; ++i) skeys[i] = keys[vals[i]];
+    // hierarchy
+    const size_t ni = (size_t)(n - 1);
+    std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), parent((size_t)2 * n, 0xffffffffu), flags(ni, 0);
+    for (int64_t i = 0; i < n - 1; ++i) {
+        const KarrasNode k = karras_node(skeys.data(), n, i);
+        left[i] = k.left; right[i] = k.right; first[i] = k.first; last[i] = k.last;
+        parent[k.left] = (uint32_t)i; parent[k.right] = (uint32_t)i;
+    }
+    // refit
+    std::vector<BBox> box((size_t)2 * n);
+    for (int64_t k = 0; k < n; ++k) {
+        box[(n - 1) + k] = tb[vals[k]];
+        if (n == 1) continue;
+        uint32_t cur = parent[(n - 1) + k];
+        for (;;) {
+            if (flags[cur]++ == 0) break;
+            box[cur] = bbox_union(box[left[cur]], box[right[cur]]);
+            if (cur == 0) break;
+            cur = parent[cur];
+        }
+    }
+    // collapse, level by level
+    std::vector<uint32_t> wide_src(lay.node_cap, 0);
+    uint32_t node_count = 1, tri_count = 0;
+    BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
+    t.box = box.data(); t.sorted_prim = vals.data();
+    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
+    o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
+    uint32_t begin = 0, end = 1, depth = 0;
+    while (begin < end) {
+        for (uint32_t w = begin; w < end; ++w) collapse_node(t, o, w, verts, nv, faces);
+        ++depth;
+        begin = end;
+        end = node_count < lay.node_cap ? node_count : lay.node_cap;
+    }
+    h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
+    for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
+    h.reserved[1] = node_count > lay.node_cap ? 1u : 0u;
+    h.reserved[2] = tri_count;
+    memcpy(blob, &h, sizeof(h));
+    return 0;
+}
+
+// mode: 0 closest (writes hit/front/tri/loc/uv), 1 any (hit), 2 count (count).  stats[0..3] as rt_trace_stats.
+extern "C" int hs_trace(const uint8_t* blob, int mode, int64_t nray, const float* o, const float* d, uint8_t* hit,
+                        uint8_t* front, int32_t* tri, float* loc, float* uv, int32_t* count, uint64_t* stats,
+                        int32_t* max_stack) {
+    const rt_blob_header* h = reinterpret_cast<const rt_blob_header*>(blob);
+    if (h->magic != RT_BLOB_MAGIC) return -4;
+    const uint8_t* tris = blob + h->tris_offset;
+    const uint8_t* nodes = blob + h->nodes_offset;
+    uint64_t sn = 0, st = 0, sh = 0;
+    int ms = 0;
+    for (int64_t r = 0; r < nray; ++r) {
+        Ray ray;
+        ray_setup(ray, o[3 * r], o[3 * r + 1], o[3 * r + 2], d[3 * r], d[3 * r + 1], d[3 * r + 2]);
+        VecStack stack;
+        if (mode == 0) {
+            ClosestVisitor<Stats> vis(RT_TMAX_DEFAULT);
+            traverse(nodes, tris, ray, vis, stack);
+            sn += vis.nodes; st += vis.tris; sh += vis.prim >= 0;
+            if (vis.prim >= 0) {
+                const float* tp = reinterpret_cast<const float*>(tris + (size_t)vis.slot * 48u);
+                TriHit th;
+                tri_test(ray, tp[0], tp[1], tp[2], tp[4], tp[5], tp[6], tp[8], tp[9], tp[10], th);
+                const HitAttr at = tri_attr(th, tp[0], tp[1], tp[2], tp[4], tp[5], tp[6], tp[8], tp[9], tp[10]);
+                hit[r] = 1; front[r] = tri_front(ray, th) ? 1 : 0; tri[r] = vis.prim;
+                loc[3 * r] = at.lx; loc[3 * r + 1] = at.ly; loc[3 * r + 2] = at.lz; uv[2 * r] = at.uv0; uv[2 * r + 1] = at.uv1;
+            } else {
+                hit[r] = 0; front[r] = 0; tri[r] = -1;
+                loc[3 * r] = loc[3 * r + 1] = loc[3 * r + 2] = 0.f; uv[2 * r] = uv[2 * r + 1] = 0.f;
+            }
+        } else if (mode == 1) {
+            AnyVisitor<Stats> vis(RT_TMAX_DEFAULT);
+            traverse(nodes, tris, ray, vis, stack);
+            sn += vis.nodes; st += vis.tris; sh += vis.found;
+            hit[r] = vis.found ? 1 : 0;
+        } else {
+            CountVisitor<Stats> vis(RT_TMAX_DEFAULT);
+            traverse(nodes, tris, ray, vis, stack);
+            sn += vis.nodes; st += vis.tris; sh += vis.count > 0;
+            count[r] = vis.count;
+        }
+        if (stack.max_sp > ms) ms = stack.max_sp;
+    }
+    if (stats) { stats[0] = sn; stats[1] = st; stats[2] = (uint64_t)nray; stats[3] = sh; }
+    if (max_stack) *max_stack = ms;
+    return 0;
+}
+
+// Structural validation of a blob (built here or copied back from the GPU):
+//  * every node index / triangle index in range, every triangle referenced exactly once,
+//    every inner node referenced exactly once (root excluded);
+//  * conservativeness: for every child slot the dequantised box contains the boxes of all
+//    triangles in the subtree below it.
+// Returns 0 when valid, otherwise a positive error code; info[0]=nodes visited, info[1]=tris visited,
+// info[2]=max depth, info[3]=sum of children over nodes.
+namespace {
+struct Checker {
+    const uint8_t* nodes; const uint8_t* tris; uint32_t n_nodes, n_tris;
+    std::vector<uint8_t> node_seen, tri_seen;
+    uint64_t children = 0; int max_depth = 0; int error = 0;
+    // returns exact box of subtree
+    BBox walk(uint32_t idx, int depth) {
+        BBox acc; acc.lx = acc.ly = acc.lz = INFINITY; acc.hx = acc.hy = acc.hz = -INFINITY; acc.pad0 = acc.pad1 = 0;
+        if (idx >= n_nodes) { error = 1; return acc; }
+        if (node_seen[idx]) { error = 2; return acc; }
+        node_seen[idx] = 1;
+        if (depth + 1 > max_depth) max_depth = depth + 1;
+        if (depth > 200) { error = 3; return acc; }
+        Node8 nd; memcpy(&nd, nodes + (size_t)idx * 80u, 80);
+        const float sx = exp2_biased(nd.ex), sy = exp2_biased(nd.ey), sz = exp2_biased(nd.ez);
+        uint32_t rel = 0;
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t meta = nd.meta[s];
+            if (meta == 0) { if (nd.imask & (1u << s)) error = 4; continue; }
+            ++children;
+            BBox cb;
+            const bool inner = (meta & 0x1fu) >= 24u;
+            if (inner) {
+                if ((meta >> 5) != 1u || (meta & 0x1fu) != 24u + (uint32_t)s || !(nd.imask & (1u << s))) error = 5;
+                cb = walk(nd.child_base + rel, depth + 1);
+                ++rel;
+            } else {
+                if (nd.imask & (1u << s)) error = 6;
+                const uint32_t un = meta >> 5, off = meta & 0x1fu;
+                const uint32_t cnt = un == 1 ? 1 : (un == 3 ? 2 : (un == 7 ? 3 : 0));
+                if (cnt == 0 || off + cnt > 24) { error = 7; continue; }
+                cb.lx = cb.ly = cb.lz = INFINITY; cb.hx = cb.hy = cb.hz = -INFINITY; cb.pad0 = cb.pad1 = 0;
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t ti = nd.tri_base + off + j;
+                    if (ti >= n_tris) { error = 8; continue; }
+                    if (tri_seen[ti]) error = 9;
+                    tri_seen[ti] = 1;
+                    const float* tp = reinterpret_cast<const float*>(tris + (size_t)ti * 48u);
+                    BBox b; // exact (not inflated) triangle box
+                    b.lx = fminf(fminf(tp[0], tp[4]), tp[8]); b.ly = fminf(fminf(tp[1], tp[5]), tp[9]); b.lz = fminf(fminf(tp[2], tp[6]), tp[10]);
+                    b.hx = fmaxf(fmaxf(tp[0], tp[4]), tp[8]); b.hy = fmaxf(fmaxf(tp[1], tp[5]), tp[9]); b.hz = fmaxf(fmaxf(tp[2], tp[6]), tp[10]);
+                    b.pad0 = b.pad1 = 0;
+                    cb = bbox_union(cb, b);
+                }
+            }
+            if (error) return acc;
+            // dequantised slot box (real arithmetic in double)
+            const double qlx = (double)nd.px + nd.qlox[s] * (double)sx, qhx = (double)nd.px + nd.qhix[s] * (double)sx;
+            const double qly = (double)nd.py + nd.qloy[s] * (double)sy, qhy = (double)nd.py + nd.qhiy[s] * (double)sy;
+            const double qlz = (double)nd.pz + nd.qloz[s] * (double)sz, qhz = (double)nd.pz + nd.qhiz[s] * (double)sz;
+            if (cb.lx <= cb.hx) {   // skip NaN / empty subtrees
+                if (qlx > cb.lx || qly > cb.ly || qlz > cb.lz || qhx < cb.hx || qhy < cb.hy || qhz < cb.hz) { error = 10; return acc; }
+            }
+            acc = bbox_union(acc, cb);
+        }
+        return acc;
+    }
+};
+}  // namespace
+
+extern "C" int hs_check_blob(const uint8_t* blob, size_t blob_bytes, uint64_t* info) {
+    if (blob_bytes < RT_BLOB_HEADER_BYTES) return 100;
+    rt_blob_header h; memcpy(&h, blob, sizeof(h));
+    if (h.magic != RT_BLOB_MAGIC || h.abi_version != RT_ABI_VERSION) return 101;
+    if (h.used_bytes > blob_bytes || h.nodes_offset + (uint64_t)h.n_nodes * 80u > blob_bytes) return 102;
+    if (h.reserved[0] != 0 || h.reserved[1] != 0) return 103;
+    Checker c; c.nodes = blob + h.nodes_offset; c.tris = blob + h.tris_offset; c.n_nodes = h.n_nodes; c.n_tris = h.n_tris;
+    c.node_seen.assign(h.n_nodes, 0); c.tri_seen.assign(h.n_tris, 0);
+    c.walk(0, 0);
+    if (c.error) return c.error;
+    for (uint32_t i = 0; i < h.n_nodes; ++i) if (!c.node_seen[i]) return 11;
+    for (uint32_t i = 0; i < h.n_tris; ++i) if (!c.tri_seen[i]) return 12;
+    if ((uint32_t)c.max_depth != h.depth) return 13;
+    if (info) { info[0] = h.n_nodes; info[1] = h.n_tris; info[2] = (uint64_t)c.max_depth; info[3] = c.children; }
+    return 0;
+}
+
+// prim ids stored in the triangle records (to check the permutation)
+extern "C" int hs_blob_prims(const uint8_t* blob, int32_t* prims_out) {
+    rt_blob_header h; memcpy(&h, blob, sizeof(h));
+    for (uint32_t i = 0; i < h.n_tris; ++i) memcpy(&prims_out[i], blob + h.tris_offset + (size_t)i * 48u + 12, 4);
+    return 0;
+}

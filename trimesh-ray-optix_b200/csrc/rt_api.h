@@ -1,0 +1,50 @@
+// rt_api.h — shared plumbing of the C ABI translation units: error reporting, blob header
+// access, launch geometry.  Nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/raymesh_b200.h"
+
+namespace rt {
+
+// thread-local message returned by rt_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define RT_CUDA_TRY(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return ::rt::set_error(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                   __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define RT_REQUIRE(cond, code, ...)                                \
+    do {                                                           \
+        if (!(cond)) return ::rt::set_error((code), __VA_ARGS__);  \
+    } while (0)
+
+struct DeviceInfo { int device; int sm_count; };
+// cached per device; sm_count == 0 when there is no usable device
+int device_info(DeviceInfo* out);
+
+inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Blob geometry derived from the triangle count alone (host side, no device read needed).
+struct BlobLayout {
+    size_t tris_offset, nodes_offset, total_bytes;
+    uint32_t node_cap;
+};
+inline BlobLayout blob_layout(int64_t n_faces) {
+    BlobLayout l;
+    l.tris_offset = RT_BLOB_HEADER_BYTES;
+    l.nodes_offset = align_up_sz(l.tris_offset + (size_t)(n_faces > 0 ? n_faces : 0) * 48u, 256);
+    // wide nodes <= n/3 + 2 (every bottom node holds > 3 triangles, every upper node has 8 children)
+    l.node_cap = (uint32_t)((n_faces > 0 ? n_faces : 0) / 3 + 2);
+    l.total_bytes = l.nodes_offset + (size_t)l.node_cap * 80u;
+    return l;
+}
+
+}  // namespace rt

@@ -1,0 +1,315 @@
+// rt_build_core.cuh — per-element logic of the BVH builder (pure functions, host/device).
+//
+// Replaces what the reference obtains from optixAccelBuild/optixAccelCompact
+// (triro/backend/ray.cpp:64-93): Morton codes, Karras' LBVH hierarchy, and the collapse of the
+// binary hierarchy into 8-wide nodes with quantised child boxes.
+#pragma once
+#include "rt_core.cuh"
+
+namespace rt {
+
+struct alignas(16) BBox {
+    float lx, ly, lz, pad0;
+    float hx, hy, hz, pad1;
+};
+
+RT_HD float fmin_nan(float a, float b) { return fminf(a, b); }   // NaN-ignoring on both host and device
+RT_HD float fmax_nan(float a, float b) { return fmaxf(a, b); }
+
+RT_HD BBox bbox_union(const BBox& a, const BBox& b) {
+    BBox r;
+    r.lx = fminf(a.lx, b.lx); r.ly = fminf(a.ly, b.ly); r.lz = fminf(a.lz, b.lz);
+    r.hx = fmaxf(a.hx, b.hx); r.hy = fmaxf(a.hy, b.hy); r.hz = fmaxf(a.hz, b.hz);
+    r.pad0 = 0.f; r.pad1 = 0.f;
+    return r;
+}
+
+RT_HD float bbox_half_area(const BBox& b) {
+    const float dx = b.hx - b.lx, dy = b.hy - b.ly, dz = b.hz - b.lz;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Triangle box, widened by a few ulps so that the watertight triangle test (which may accept
+// rays a rounding error outside the exact triangle) never reports a hit outside the box.
+RT_HD BBox tri_bbox(float v0x, float v0y, float v0z, float v1x, float v1y, float v1z, float v2x, float v2y,
+                    float v2z) {
+    BBox b;
+    b.lx = fminf(fminf(v0x, v1x), v2x); b.ly = fminf(fminf(v0y, v1y), v2y); b.lz = fminf(fminf(v0z, v1z), v2z);
+    b.hx = fmaxf(fmaxf(v0x, v1x), v2x); b.hy = fmaxf(fmaxf(v0y, v1y), v2y); b.hz = fmaxf(fmaxf(v0z, v1z), v2z);
+    const float k = 6.0e-7f, tiny = 1.0e-30f;
+    b.lx -= fabsf(b.lx) * k + tiny; b.ly -= fabsf(b.ly) * k + tiny; b.lz -= fabsf(b.lz) * k + tiny;
+    b.hx += fabsf(b.hx) * k + tiny; b.hy += fabsf(b.hy) * k + tiny; b.hz += fabsf(b.hz) * k + tiny;
+    b.pad0 = 0.f; b.pad1 = 0.f;
+    return b;
+}
+
+// ------------------------------------------------------------------ Morton codes (21 bits per axis)
+RT_HD uint64_t expand21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | (x << 32)) & 0x001f00000000ffffull;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+RT_HD uint64_t morton63(float cx, float cy, float cz, const float lo[3], const float inv_ext[3]) {
+    const float scale = 2097152.0f;   // 2^21
+    float fx = (cx - lo[0]) * inv_ext[0] * scale;
+    float fy = (cy - lo[1]) * inv_ext[1] * scale;
+    float fz = (cz - lo[2]) * inv_ext[2] * scale;
+    fx = fminf(fmaxf(fx, 0.0f), 2097151.0f);   // NaN -> 0
+    fy = fminf(fmaxf(fy, 0.0f), 2097151.0f);
+    fz = fminf(fmaxf(fz, 0.0f), 2097151.0f);
+    if (!(fx == fx)) fx = 0.0f;
+    if (!(fy == fy)) fy = 0.0f;
+    if (!(fz == fz)) fz = 0.0f;
+    return expand21((uint64_t)fx) | (expand21((uint64_t)fy) << 1) | (expand21((uint64_t)fz) << 2);
+}
+
+// ------------------------------------------------------------------ Karras 2012 hierarchy
+#if defined(__CUDA_ARCH__)
+RT_HD int clz64(uint64_t x) { return __clzll((long long)x); }
+RT_HD int clz32u(uint32_t x) { return __clz((int)x); }
+#else
+RT_HD int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
+RT_HD int clz32u(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+#endif
+
+// length of the common prefix of keys i and j (index as tie-break); -1 when j is out of range
+RT_HD int karras_delta(const uint64_t* __restrict__ keys, int64_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + clz32u((uint32_t)i ^ (uint32_t)j);
+    return clz64(a ^ b);
+}
+
+// Node references: internal node k -> k (0..n-2); leaf at sorted position k -> (n-1) + k.
+struct KarrasNode { uint32_t left, right, first, last; };
+
+RT_HD KarrasNode karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i) {
+    const int dl = karras_delta(keys, n, i, i - 1), dr = karras_delta(keys, n, i, i + 1);
+    const int64_t d = dr > dl ? 1 : -1;
+    const int dmin = dr > dl ? dl : dr;
+    int64_t lmax = 2;
+    while (karras_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int64_t l = 0;
+    for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
+        if (karras_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int64_t j = i + l * d;
+    const int dnode = karras_delta(keys, n, i, j);
+    int64_t s = 0;
+    for (int64_t t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (karras_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
+    const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    KarrasNode k;
+    k.left = (uint32_t)(lo == gamma ? (n - 1) + gamma : gamma);
+    k.right = (uint32_t)(hi == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
+    k.first = (uint32_t)lo;
+    k.last = (uint32_t)hi;
+    return k;
+}
+
+// ------------------------------------------------------------------ collapse to BVH8
+struct BinaryTree {
+    int64_t n;                    // triangles (= leaves)
+    const uint32_t* left;         // [n-1]
+    const uint32_t* right;        // [n-1]
+    const uint32_t* first;        // [n-1] first sorted position covered
+    const uint32_t* last;         // [n-1]
+    const BBox* box;              // [2n-1] internal boxes then leaf boxes
+    const uint32_t* sorted_prim;  // [n] triangle id at each sorted position
+};
+
+RT_HD uint32_t bt_count(const BinaryTree& t, uint32_t ref) {
+    return ref >= (uint32_t)(t.n - 1) ? 1u : t.last[ref] - t.first[ref] + 1u;
+}
+RT_HD uint32_t bt_first(const BinaryTree& t, uint32_t ref) {
+    return ref >= (uint32_t)(t.n - 1) ? ref - (uint32_t)(t.n - 1) : t.first[ref];
+}
+
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+RT_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+#endif
+
+// L1-bypassing load for data produced earlier in the same (cooperative) kernel
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t load_cg_u32(const uint32_t* p) { return __ldcg(p); }
+#else
+RT_HD uint32_t load_cg_u32(const uint32_t* p) { return *p; }
+#endif
+
+RT_HD float exp2_biased(uint32_t e) { return as_float(e << 23); }
+
+// Smallest biased exponent e (1..254) with 255 * 2^(e-127) >= ext.
+RT_HD uint32_t quant_exponent(float ext) {
+    if (!(ext > 0.0f)) return 1u;
+    int k;
+    const float m = frexpf(ext / 255.0f, &k);   // ext/255 = m * 2^k, m in [0.5, 1)
+    (void)m;
+    int e = k + 127;                            // 2^k >= ext/255
+    if (e < 1) e = 1;
+    if (e > 254) e = 254;
+    return (uint32_t)e;
+}
+
+struct CollapseOut {
+    uint8_t* nodes;          // Node8 array (80 B each)
+    uint8_t* tris;           // TriRecord array (48 B each)
+    uint32_t* wide_src;      // binary reference expanded by each wide node
+    uint32_t* node_count;    // atomic allocators
+    uint32_t* tri_count;
+    uint32_t node_cap;
+};
+
+// Builds wide node `w` from the binary subtree `wide_src[w]`.  Greedy surface-area expansion:
+// starting from the two children, repeatedly replace the child with the largest box that is
+// still expandable (an inner node covering more than kLeafMaxTris triangles) by its own two
+// children until there are 8 children.  Subtrees with <= kLeafMaxTris triangles become leaf
+// slots (their triangles are contiguous in Morton order).
+RT_HD bool bt_expandable(const BinaryTree& t, uint32_t ref) {
+    return ref < (uint32_t)(t.n - 1) && bt_count(t, ref) > (uint32_t)kLeafMaxTris;
+}
+RT_HD float bt_area(const BinaryTree& t, uint32_t ref) {
+    const float a = bbox_half_area(t.box[ref]);
+    return a >= 0.0f ? a : 0.0f;   // NaN / negative -> 0
+}
+RT_HD int32_t clamp_index(int32_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? (int32_t)(n - 1) : i); }
+
+RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, const float* __restrict__ verts,
+                         int64_t n_verts, const int32_t* __restrict__ faces) {
+    uint32_t ref[8];
+    float area[8];
+    bool inner[8];
+    int k = 0;
+    const uint32_t src = load_cg_u32(&o.wide_src[w]);
+    const BBox nb = t.box[src];
+    if (t.n <= (int64_t)kLeafMaxTris) {
+        // whole mesh fits one leaf slot (n = 1..3): root with a single leaf child
+        ref[0] = src; area[0] = 0.0f; inner[0] = false; k = 1;
+    } else {
+        ref[0] = t.left[src]; ref[1] = t.right[src]; k = 2;
+        for (int i = 0; i < 2; ++i) { inner[i] = bt_expandable(t, ref[i]); area[i] = bt_area(t, ref[i]); }
+        while (k < 8) {
+            int best = -1; float ba = -1.0f;
+            for (int i = 0; i < k; ++i)
+                if (inner[i] && area[i] > ba) { best = i; ba = area[i]; }
+            if (best < 0) break;
+            const uint32_t b = ref[best];
+            const uint32_t l = t.left[b], r = t.right[b];
+            ref[best] = l; inner[best] = bt_expandable(t, l); area[best] = bt_area(t, l);
+            ref[k] = r; inner[k] = bt_expandable(t, r); area[k] = bt_area(t, r);
+            ++k;
+        }
+    }
+    // child boxes, kinds
+    BBox cb[8];
+    uint32_t n_inner = 0, n_tris = 0;
+    for (int i = 0; i < k; ++i) {
+        cb[i] = t.box[ref[i]];
+        if (inner[i]) ++n_inner; else n_tris += bt_count(t, ref[i]);
+    }
+    // greedy slot assignment: child i goes to the free slot whose octant direction agrees
+    // best with (child centre - node centre); traversal visits slots in ray-octant order.
+    const float ncx = 0.5f * (nb.lx + nb.hx), ncy = 0.5f * (nb.ly + nb.hy), ncz = 0.5f * (nb.lz + nb.hz);
+    int child_in_slot[8];
+    for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
+    for (int i = 0; i < k; ++i) {
+        const float vx = 0.5f * (cb[i].lx + cb[i].hx) - ncx, vy = 0.5f * (cb[i].ly + cb[i].hy) - ncy,
+                    vz = 0.5f * (cb[i].lz + cb[i].hz) - ncz;
+        int bs = -1; float bsc = 0.0f;
+        for (int s = 0; s < 8; ++s) {
+            if (child_in_slot[s] >= 0) continue;
+            const float sc = ((s & 1) ? vx : -vx) + ((s & 2) ? vy : -vy) + ((s & 4) ? vz : -vz);
+            if (bs < 0 || sc > bsc) { bs = s; bsc = sc; }
+        }
+        child_in_slot[bs] = i;
+    }
+    const uint32_t child_base = n_inner ? atomic_add_u32(o.node_count, n_inner) : 0u;
+    const uint32_t tri_base = n_tris ? atomic_add_u32(o.tri_count, n_tris) : 0u;
+
+    // quantisation frame
+    const float p[3] = {nb.lx, nb.ly, nb.lz};
+    const float hi3[3] = {nb.hx, nb.hy, nb.hz};
+    uint32_t e[3];
+    for (int a = 0; a < 3; ++a) {
+        e[a] = quant_exponent(hi3[a] - p[a]);
+        // make sure every child's upper plane is representable (<= 255 steps)
+        for (;;) {
+            const double sc = (double)exp2_biased(e[a]);
+            bool ok = true;
+            for (int i = 0; i < k; ++i) {
+                const float ch = a == 0 ? cb[i].hx : (a == 1 ? cb[i].hy : cb[i].hz);
+                if ((double)p[a] + 255.0 * sc < (double)ch) { ok = false; break; }
+            }
+            if (ok || e[a] >= 254u) break;
+            ++e[a];
+        }
+    }
+    Node8 nd;
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2];
+    nd.child_base = child_base;
+    nd.tri_base = tri_base;
+    uint32_t imask = 0, rel = 0, toff = 0;
+    for (int s = 0; s < 8; ++s) {
+        const int i = child_in_slot[s];
+        if (i < 0) {
+            nd.meta[s] = 0;
+            nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;   // inverted box: never hit
+            nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+            continue;
+        }
+        uint8_t ql[3], qh[3];
+        for (int a = 0; a < 3; ++a) {
+            const float cl = a == 0 ? cb[i].lx : (a == 1 ? cb[i].ly : cb[i].lz);
+            const float ch = a == 0 ? cb[i].hx : (a == 1 ? cb[i].hy : cb[i].hz);
+            const double sc = (double)exp2_biased(e[a]);
+            double fl = floor(((double)cl - (double)p[a]) / sc);
+            if (!(fl >= 0.0)) fl = 0.0;
+            if (fl > 255.0) fl = 255.0;
+            while (fl > 0.0 && (double)p[a] + fl * sc > (double)cl) fl -= 1.0;
+            double fh = ceil(((double)ch - (double)p[a]) / sc);
+            if (!(fh >= 0.0)) fh = 0.0;
+            if (fh > 255.0) fh = 255.0;
+            while (fh < 255.0 && (double)p[a] + fh * sc < (double)ch) fh += 1.0;
+            ql[a] = (uint8_t)fl; qh[a] = (uint8_t)fh;
+        }
+        nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
+        nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
+        if (inner[i]) {
+            imask |= 1u << s;
+            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            if (child_base + rel < o.node_cap) o.wide_src[child_base + rel] = ref[i];
+            ++rel;
+        } else {
+            const uint32_t cnt = bt_count(t, ref[i]);
+            const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+            nd.meta[s] = (uint8_t)((unary << 5) | toff);
+            const uint32_t f0 = bt_first(t, ref[i]);
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t prim = t.sorted_prim[f0 + j];
+                const int32_t i0 = clamp_index(faces[3 * (size_t)prim], n_verts),
+                              i1 = clamp_index(faces[3 * (size_t)prim + 1], n_verts),
+                              i2 = clamp_index(faces[3 * (size_t)prim + 2], n_verts);
+                TriRecord tr;
+                tr.v0x = verts[3 * (size_t)i0]; tr.v0y = verts[3 * (size_t)i0 + 1]; tr.v0z = verts[3 * (size_t)i0 + 2];
+                tr.v1x = verts[3 * (size_t)i1]; tr.v1y = verts[3 * (size_t)i1 + 1]; tr.v1z = verts[3 * (size_t)i1 + 2];
+                tr.v2x = verts[3 * (size_t)i2]; tr.v2y = verts[3 * (size_t)i2 + 1]; tr.v2z = verts[3 * (size_t)i2 + 2];
+                tr.prim = (int32_t)prim; tr.pad1 = 0; tr.pad2 = 0;
+                *reinterpret_cast<TriRecord*>(o.tris + (size_t)(tri_base + toff + j) * 48u) = tr;
+            }
+            toff += cnt;
+        }
+    }
+    nd.imask = (uint8_t)imask;
+    if (w < o.node_cap) *reinterpret_cast<Node8*>(o.nodes + (size_t)w * 80u) = nd;
+}
+
+}  // namespace rt

@@ -1,0 +1,274 @@
+// rt_compact.cu — single-pass prefix sums (decoupled look-back) and the order-preserving
+// scatter kernels built on them: stream compaction of closest-hit results and packing of
+// all-hits records.
+//
+// Replaces, in the reference:
+//   * stream_compaction=True in RayMeshIntersector.intersects_closest / intersects_id
+//     (triro/ray/ray_optix.py:142-144, :219-223): a CPU arange + H2D copy + five boolean-mask
+//     gathers, each with its own nonzero() and host sync;
+//   * the clamp / cumsum / item() / cat chain of intersectsLocation (triro/backend/ray.cpp:333-342)
+//     and the per-ray copy loop of __raygen__intersectsLocation (triro/backend/shaders.cu:241-245).
+#include "rt_api.h"
+
+namespace rt {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+static_assert(kScanTile == RT_COMPACT_TILE, "tile size is part of the ABI");
+
+constexpr unsigned long long kStAggregate = 1ull << 62;
+constexpr unsigned long long kStPrefix = 2ull << 62;
+constexpr unsigned long long kStValue = (1ull << 62) - 1ull;
+
+struct ScanWorkspace {
+    uint32_t* tile_counter;            // 256 B slot
+    unsigned long long* status;        // [tiles]
+    long long* tile_prefix;            // [tiles] exclusive prefix of each tile
+    int64_t tiles;
+};
+
+static int64_t scan_tiles(int64_t n) { return n <= 0 ? 0 : (n + kScanTile - 1) / kScanTile; }
+
+size_t scan_workspace_bytes(int64_t n) {
+    const int64_t t = scan_tiles(n);
+    return 256 + align_up_sz((size_t)t * 8, 256) + align_up_sz((size_t)t * 8, 256);
+}
+
+static ScanWorkspace carve_scan(void* ws, int64_t n) {
+    ScanWorkspace w;
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    w.tiles = scan_tiles(n);
+    w.tile_counter = reinterpret_cast<uint32_t*>(p);
+    w.status = reinterpret_cast<unsigned long long*>(p + 256);
+    w.tile_prefix = reinterpret_cast<long long*>(p + 256 + align_up_sz((size_t)w.tiles * 8, 256));
+    return w;
+}
+
+// eight consecutive items of a thread
+__device__ __forceinline__ void load8(const uint8_t* in, int64_t i0, int64_t n, int v[kScanItems]) {
+    if (i0 + kScanItems <= n) {
+        const uint2 w = *reinterpret_cast<const uint2*>(in + i0);   // i0 is a multiple of 8
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = ((w.x >> (8 * j)) & 0xffu) ? 1 : 0; v[4 + j] = ((w.y >> (8 * j)) & 0xffu) ? 1 : 0; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) v[j] = (i0 + j < n && in[i0 + j]) ? 1 : 0;
+    }
+}
+__device__ __forceinline__ void load8(const int32_t* in, int64_t i0, int64_t n, int v[kScanItems]) {
+    if (i0 + kScanItems <= n) {
+        const int4 a = *reinterpret_cast<const int4*>(in + i0);
+        const int4 b = *reinterpret_cast<const int4*>(in + i0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+    }
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive value, *total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int x, int* total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    __shared__ int block_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) {
+        const int s = warp_sums[i];
+        if (i < warp) base += s;
+    }
+    if (threadIdx.x == kScanThreads - 1) block_total = base + incl;
+    __syncthreads();
+    *total = block_total;
+    return base + incl - x;
+}
+
+// One tile per CTA (claimed in launch order); publishes the tile aggregate, resolves its
+// exclusive prefix by a warp-wide look-back, stores it in tile_prefix[].
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const T* __restrict__ in, int64_t n,
+                                                             uint32_t* tile_counter,
+                                                             volatile unsigned long long* status,
+                                                             long long* __restrict__ tile_prefix,
+                                                             long long* __restrict__ total_out) {
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    int v[kScanItems];
+    load8(in, tile * kScanTile + (int64_t)threadIdx.x * kScanItems, n, v);
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) sum += v[j];
+    int tile_total;
+    block_exclusive_scan(sum, &tile_total);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) status[0] = kStPrefix | (unsigned long long)tile_total;
+        } else {
+            if (lane == 0) status[tile] = kStAggregate | (unsigned long long)tile_total;
+            int64_t look = tile - 1;
+            for (;;) {
+                const int64_t idx = look - lane;
+                unsigned long long s = kStPrefix;             // virtual tiles before 0 contribute a zero prefix
+                if (idx >= 0) {
+                    do { s = status[idx]; } while ((s & ~kStValue) == 0ull);
+                }
+                const unsigned is_prefix = __ballot_sync(0xffffffffu, (s & ~kStValue) == kStPrefix);
+                const int first = __ffs((int)is_prefix) - 1;  // nearest predecessor holding an inclusive prefix
+                unsigned long long contrib = (is_prefix == 0u || lane <= first) ? (s & kStValue) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                excl += contrib;
+                if (is_prefix) break;
+                look -= 32;
+            }
+            if (lane == 0) status[tile] = kStPrefix | ((excl + (unsigned long long)tile_total) & kStValue);
+        }
+        if (lane == 0) {
+            tile_prefix[tile] = (long long)excl;
+            if (tile == (n + kScanTile - 1) / kScanTile - 1) *total_out = (long long)excl + tile_total;
+        }
+    }
+}
+
+template <typename T>
+static int scan_generic(const char* fn, const T* in, int64_t n, void* workspace, size_t workspace_bytes,
+                        int64_t* total_dev, cudaStream_t stream) {
+    RT_REQUIRE(total_dev != nullptr, RT_ERR_INVALID, "%s: null total", fn);
+    if (n == 0) {
+        RT_CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
+        return RT_OK;
+    }
+    RT_REQUIRE(in && workspace, RT_ERR_INVALID, "%s: null pointer", fn);
+    RT_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)workspace & 255) == 0, RT_ERR_INVALID, "%s: misaligned buffer", fn);
+    RT_REQUIRE(workspace_bytes >= scan_workspace_bytes(n), RT_ERR_SIZE, "%s: workspace too small", fn);
+    ScanWorkspace w = carve_scan(workspace, n);
+    RT_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256 + align_up_sz((size_t)w.tiles * 8, 256), stream));
+    k_scan_tiles<T><<<(unsigned)w.tiles, kScanThreads, 0, stream>>>(in, n, w.tile_counter, w.status, w.tile_prefix,
+                                                                    reinterpret_cast<long long*>(total_dev));
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+int scan_counts_i32(const int32_t* counts, int64_t n, void* workspace, size_t workspace_bytes, int64_t* total_dev,
+                    cudaStream_t stream) {
+    return scan_generic<int32_t>("rt_allhits_trace", counts, n, workspace, workspace_bytes, total_dev, stream);
+}
+
+// ------------------------------------------------------------------ scatter kernels (one CTA per tile)
+__global__ void __launch_bounds__(kScanThreads) k_compact_scatter(
+    const uint8_t* __restrict__ hit, int64_t n, const long long* __restrict__ tile_prefix,
+    const uint8_t* __restrict__ front, const int32_t* __restrict__ tri, const float* __restrict__ loc,
+    const float* __restrict__ uv, uint8_t* __restrict__ front_out, int32_t* __restrict__ ray_out,
+    int32_t* __restrict__ tri_out, float* __restrict__ loc_out, float* __restrict__ uv_out) {
+    const int64_t tile = blockIdx.x;
+    const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    load8(hit, i0, n, v);
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) sum += v[j];
+    int tile_total;
+    const int excl = block_exclusive_scan(sum, &tile_total);
+    int64_t dst = tile_prefix[tile] + excl;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (v[j]) {
+            const int64_t r = i0 + j;
+            front_out[dst] = front[r];
+            ray_out[dst] = (int32_t)r;
+            tri_out[dst] = tri[r];
+            loc_out[3 * dst] = loc[3 * r]; loc_out[3 * dst + 1] = loc[3 * r + 1]; loc_out[3 * dst + 2] = loc[3 * r + 2];
+            uv_out[2 * dst] = uv[2 * r]; uv_out[2 * dst + 1] = uv[2 * r + 1];
+            ++dst;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_allhits_scatter(
+    int64_t n, int max_hits, const int32_t* __restrict__ count, const uint4* __restrict__ staging,
+    const long long* __restrict__ tile_prefix, float* __restrict__ loc_out, int32_t* __restrict__ ray_out,
+    int32_t* __restrict__ tri_out) {
+    const int64_t tile = blockIdx.x;
+    const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    load8(count, i0, n, v);
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) sum += v[j];
+    int tile_total;
+    const int excl = block_exclusive_scan(sum, &tile_total);
+    int64_t dst = tile_prefix[tile] + excl;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const int64_t r = i0 + j;
+        for (int k = 0; k < v[j]; ++k) {
+            const uint4 rec = staging[(size_t)r * max_hits + k];
+            ray_out[dst] = (int32_t)r;
+            tri_out[dst] = (int32_t)rec.x;
+            loc_out[3 * dst] = __uint_as_float(rec.y);
+            loc_out[3 * dst + 1] = __uint_as_float(rec.z);
+            loc_out[3 * dst + 2] = __uint_as_float(rec.w);
+            ++dst;
+        }
+    }
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" int rt_compact_sizes(int64_t nray, size_t* workspace_bytes) {
+    RT_REQUIRE(nray >= 0 && workspace_bytes, RT_ERR_INVALID, "rt_compact_sizes: bad arguments");
+    *workspace_bytes = scan_workspace_bytes(nray);
+    return RT_OK;
+}
+
+extern "C" int rt_compact_scan(const uint8_t* hit, int64_t nray, void* workspace, size_t workspace_bytes,
+                               int64_t* total_dev, void* stream) {
+    RT_REQUIRE(nray >= 0, RT_ERR_INVALID, "rt_compact_scan: negative ray count");
+    return scan_generic<uint8_t>("rt_compact_scan", hit, nray, workspace, workspace_bytes, total_dev,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* workspace, const uint8_t* front,
+                                  const int32_t* tri_idx, const float* loc, const float* uv, uint8_t* front_out,
+                                  int32_t* ray_idx_out, int32_t* tri_idx_out, float* loc_out, float* uv_out,
+                                  void* stream) {
+    RT_REQUIRE(nray >= 0, RT_ERR_INVALID, "rt_compact_scatter: negative ray count");
+    if (nray == 0) return RT_OK;
+    RT_REQUIRE(hit && workspace && front && tri_idx && loc && uv, RT_ERR_INVALID, "rt_compact_scatter: null input");
+    // outputs may be null only when nothing was hit; the kernel then never dereferences them
+    ScanWorkspace w = carve_scan(const_cast<void*>(workspace), nray);
+    k_compact_scatter<<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+        hit, nray, w.tile_prefix, front, tri_idx, loc, uv, front_out, ray_idx_out, tri_idx_out, loc_out, uv_out);
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+extern "C" int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
+                                  const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
+                                  void* stream) {
+    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE, RT_ERR_INVALID,
+               "rt_allhits_scatter: bad arguments");
+    if (nray == 0) return RT_OK;
+    RT_REQUIRE(count_clamped && staging && workspace, RT_ERR_INVALID, "rt_allhits_scatter: null input");
+    ScanWorkspace w = carve_scan(const_cast<void*>(workspace), nray);
+    k_allhits_scatter<<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+        nray, max_hits, count_clamped, reinterpret_cast<const uint4*>(staging), w.tile_prefix, loc_out, ray_idx_out,
+        tri_idx_out);
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}

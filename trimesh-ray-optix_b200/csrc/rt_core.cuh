@@ -1,0 +1,264 @@
+// rt_core.cuh — data layout and per-ray arithmetic of the B200 ray/mesh intersector.
+//
+// Everything in this header is a pure function of its arguments (RT_HD = __host__ __device__)
+// so that the same source can be stepped through by the host-side simulator under
+// tests/hostsim/ (a debugging harness, never linked into libtriro_b200.so).
+//
+// What this replaces in the reference: the arithmetic that lives inside the closed OptiX
+// runtime behind optixTrace (triro/backend/shaders.cu:86,112,163,191,238) — BVH traversal and
+// the watertight ray/triangle test — plus the closest-hit attribute code of
+// shaders.cu:137-153.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
+
+namespace rt {
+
+// ------------------------------------------------------------------ exact float ops
+// The triangle test must be evaluated with a fixed sequence of IEEE-754 binary32
+// operations: (1) the edge functions of two triangles sharing an edge must be exact
+// negations of each other (watertightness, Woop/Benthin/Wald 2013) which an FMA contraction
+// chosen by the compiler would break; (2) the float32 mirror in oracle/ reproduces the
+// sequence bit for bit.
+#if defined(__CUDA_ARCH__)
+RT_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+RT_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+RT_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+RT_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+RT_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+RT_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+RT_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+// host build is compiled with -ffp-contract=off
+RT_HD float fmul(float a, float b) { return a * b; }
+RT_HD float fadd(float a, float b) { return a + b; }
+RT_HD float fsub(float a, float b) { return a - b; }
+RT_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+RT_HD float fdiv(float a, float b) { return a / b; }
+RT_HD double dmul(double a, double b) { return a * b; }
+RT_HD double dsub(double a, double b) { return a - b; }
+#endif
+
+RT_HD float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+
+#if defined(__CUDA_ARCH__)
+RT_HD float as_float(uint32_t u) { return __uint_as_float(u); }
+#else
+RT_HD float as_float(uint32_t u) { union { uint32_t u; float f; } c; c.u = u; return c.f; }
+#endif
+
+// ------------------------------------------------------------------ layout in HBM
+// Blob = [header 256 B][triangle records 48 B each][BVH8 nodes 80 B each].
+// All sections are 16-byte aligned so every fetch is a 128-bit ld.global.nc.
+
+constexpr int kLeafMaxTris = 3;    // triangles per leaf slot (unary-coded in 3 bits)
+constexpr int kNodeMaxTris = 24;   // 8 slots x 3
+constexpr int kMaxDepth = 60;      // wide-tree levels the traversal stack can hold
+
+struct alignas(16) TriRecord {     // 48 B: three 128-bit loads
+    float v0x, v0y, v0z;
+    int32_t prim;                  // row of `faces` (reference: optixGetPrimitiveIndex)
+    float v1x, v1y, v1z;
+    uint32_t pad1;
+    float v2x, v2y, v2z;
+    uint32_t pad2;
+};
+static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
+
+// Compressed 8-wide node after Ylitie, Karras, Laine 2017 (80 B: five 128-bit loads).
+// Child boxes are quantised to 8 bits per plane relative to (p, 2^e):
+//   plane = p + q * 2^(e-127)    (lo planes rounded down, hi planes rounded up)
+// meta[i]: 0 = empty slot; inner child = 0b001_sssss with sssss = 24 + slot;
+//          leaf = unary triangle count (001/011/111) in the top 3 bits, triangle offset
+//          (relative to tri_base) in the low 5 bits.
+struct alignas(16) Node8 {
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t child_base;           // index of the first inner child (children are contiguous)
+    uint32_t tri_base;             // index of this node's first triangle record
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8], qloz[8];
+    uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+struct U4 { uint32_t x, y, z, w; };
+
+// ------------------------------------------------------------------ ray set-up
+struct Ray {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    // watertight test set-up
+    int kz;
+    float Sx, Sy, Sz;
+    float okx, oky, okz;           // origin permuted to (kx, ky, kz)
+    // slab test set-up
+    float idx, idy, idz;           // 1/d with zero components replaced by +-tiny
+    uint32_t octinv;               // 7 - octant, octant bit a = (d_a < 0)
+};
+
+RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    r.dx = dx; r.dy = dy; r.dz = dz;
+    // kz = dimension where |d| is maximal (first maximum in x,y,z order)
+    int kz = 0;
+    float m = fabsf(dx);
+    if (fabsf(dy) > m) { kz = 1; m = fabsf(dy); }
+    if (fabsf(dz) > m) { kz = 2; }
+    r.kz = kz;
+    const int kx = kz == 2 ? 0 : kz + 1;
+    const int ky = kx == 2 ? 0 : kx + 1;
+    const float dkx = sel3(kx, dx, dy, dz), dky = sel3(ky, dx, dy, dz), dkz = sel3(kz, dx, dy, dz);
+    // (the Woop kx/ky swap for d[kz] < 0 only flips the sign of U,V,W; it is folded into
+    //  the front-face decision instead, see tri_front())
+    r.Sx = fdiv(dkx, dkz);
+    r.Sy = fdiv(dky, dkz);
+    r.Sz = fdiv(1.0f, dkz);
+    r.okx = sel3(kx, ox, oy, oz);
+    r.oky = sel3(ky, ox, oy, oz);
+    r.okz = sel3(kz, ox, oy, oz);
+    const float tiny = 1e-20f;
+    const float sx = fabsf(dx) < tiny ? (signbit(dx) ? -tiny : tiny) : dx;
+    const float sy = fabsf(dy) < tiny ? (signbit(dy) ? -tiny : tiny) : dy;
+    const float sz = fabsf(dz) < tiny ? (signbit(dz) ? -tiny : tiny) : dz;
+    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
+    const uint32_t oct = (sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u);
+    r.octinv = 7u - oct;
+}
+
+// ------------------------------------------------------------------ watertight triangle test
+// Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection", JCGT 2013, in binary32 with a
+// binary64 fallback when an edge function is exactly zero.  Reports a hit iff the sheared
+// origin lies inside or on the boundary of the triangle and det != 0; returns
+//   t = T/det, and the unnormalised barycentrics U (weight of v0), V (v1), W (v2), det = U+V+W.
+// The caller applies the open interval 0 < t < tmax (reference: tmin 0, tmax 1e7).
+struct TriHit { float t, U, V, W, det; };
+
+RT_HD bool tri_test(const Ray& r, float v0x, float v0y, float v0z, float v1x, float v1y, float v1z,
+                    float v2x, float v2y, float v2z, TriHit& h) {
+    const int kz = r.kz;
+    const int kx = kz == 2 ? 0 : kz + 1;
+    const int ky = kx == 2 ? 0 : kx + 1;
+    const float Akx = fsub(sel3(kx, v0x, v0y, v0z), r.okx);
+    const float Aky = fsub(sel3(ky, v0x, v0y, v0z), r.oky);
+    const float Akz = fsub(sel3(kz, v0x, v0y, v0z), r.okz);
+    const float Bkx = fsub(sel3(kx, v1x, v1y, v1z), r.okx);
+    const float Bky = fsub(sel3(ky, v1x, v1y, v1z), r.oky);
+    const float Bkz = fsub(sel3(kz, v1x, v1y, v1z), r.okz);
+    const float Ckx = fsub(sel3(kx, v2x, v2y, v2z), r.okx);
+    const float Cky = fsub(sel3(ky, v2x, v2y, v2z), r.oky);
+    const float Ckz = fsub(sel3(kz, v2x, v2y, v2z), r.okz);
+    const float Ax = ffma(-r.Sx, Akz, Akx), Ay = ffma(-r.Sy, Akz, Aky);
+    const float Bx = ffma(-r.Sx, Bkz, Bkx), By = ffma(-r.Sy, Bkz, Bky);
+    const float Cx = ffma(-r.Sx, Ckz, Ckx), Cy = ffma(-r.Sy, Ckz, Cky);
+    float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+    float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+    float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        const double Ud = dsub(dmul((double)Cx, (double)By), dmul((double)Cy, (double)Bx));
+        const double Vd = dsub(dmul((double)Ax, (double)Cy), dmul((double)Ay, (double)Cx));
+        const double Wd = dsub(dmul((double)Bx, (double)Ay), dmul((double)By, (double)Ax));
+        if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
+        U = (float)Ud; V = (float)Vd; W = (float)Wd;
+    } else {
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    }
+    const float det = fadd(fadd(U, V), W);
+    if (!(det != 0.0f)) return false;   // also rejects NaN
+    const float Az = fmul(r.Sz, Akz), Bz = fmul(r.Sz, Bkz), Cz = fmul(r.Sz, Ckz);
+    const float T = ffma(U, Az, ffma(V, Bz, fmul(W, Cz)));
+    h.t = fdiv(T, det);
+    h.U = U; h.V = V; h.W = W; h.det = det;
+    return true;
+}
+
+// front face = triangle seen counter-clockwise from the ray origin, i.e.
+// dot(d, (v1-v0) x (v2-v0)) < 0 (reference: optixIsFrontFaceHit, shaders.cu:151).
+// With the fixed cyclic (kx,ky,kz) the sheared edge functions carry the sign of
+// -dot(d, n) * sign(d[kz]) ... so: front <=> (det > 0) == (d[kz] > 0).
+RT_HD bool tri_front(const Ray& r, const TriHit& h) {
+    const float dkz = sel3(r.kz, r.dx, r.dy, r.dz);
+    return (h.det > 0.0f) == (dkz > 0.0f);
+}
+
+// Closest-hit attributes exactly as the reference computes them (shaders.cu:137-153):
+//   (u,v) = OptiX barycentrics = weights of v1, v2;  loc = u*v1 + v*v2 + (1-u-v)*v0;
+//   returned uv = (1-u-v, u) = (weight of v0, weight of v1).
+struct HitAttr { float lx, ly, lz, uv0, uv1; };
+RT_HD HitAttr tri_attr(const TriHit& h, float v0x, float v0y, float v0z, float v1x, float v1y, float v1z,
+                       float v2x, float v2y, float v2z) {
+    const float bu = fdiv(h.V, h.det);
+    const float bv = fdiv(h.W, h.det);
+    const float w0 = fsub(fsub(1.0f, bu), bv);
+    HitAttr a;
+    a.lx = ffma(bu, v1x, ffma(bv, v2x, fmul(w0, v0x)));
+    a.ly = ffma(bu, v1y, ffma(bv, v2y, fmul(w0, v0y)));
+    a.lz = ffma(bu, v1z, ffma(bv, v2z, fmul(w0, v0z)));
+    a.uv0 = w0;
+    a.uv1 = bu;
+    return a;
+}
+
+// ------------------------------------------------------------------ BVH8 node test
+// Returns the 32-bit hit mask of Ylitie et al.: bits 24..31 = inner children ordered by
+// traversal priority (slot ^ octinv), bits 0..23 = triangles of hit leaf slots.
+// The slab test is conservative: with a = 2^e * idir, b = (p - o) * idir,
+//   t_plane = q*a + b  has |error| <= ~5u(256|a| + |b|), u = 2^-24, which is added to the far
+// and subtracted from the near planes.  NaNs drop out of fminf/fmaxf, which only widens.
+RT_HD float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+
+RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
+                         float tmin, float tmax) {
+    const float px = as_float(n0.x), py = as_float(n0.y), pz = as_float(n0.z);
+    const float sx = as_float((n0.w & 0xffu) << 23);
+    const float sy = as_float(((n0.w >> 8) & 0xffu) << 23);
+    const float sz = as_float(((n0.w >> 16) & 0xffu) << 23);
+    const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
+    const float bx = (px - r.ox) * r.idx, by = (py - r.oy) * r.idy, bz = (pz - r.oz) * r.idz;
+    const float ku = 3.0e-7f;   // 5 * 2^-24
+    const float ex = ku * (256.0f * fabsf(ax) + fabsf(bx));
+    const float ey = ku * (256.0f * fabsf(ay) + fabsf(by));
+    const float ez = ku * (256.0f * fabsf(az) + fabsf(bz));
+    const float bnx = bx - ex, bfx = bx + ex;
+    const float bny = by - ey, bfy = by + ey;
+    const float bnz = bz - ez, bfz = bz + ez;
+    // near/far plane bytes by ray octant: d >= 0 -> near = lo, far = hi
+    const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
+    // words: n2 = (qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7])
+    //        n3 = (qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7])
+    //        n4 = (qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7])
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+        const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+        const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
+        const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
+        const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
+        const uint32_t meta4 = half ? n1.w : n1.z;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float tnx = fmaf(byte_f(nx, i), ax, bnx), tfx = fmaf(byte_f(fx, i), ax, bfx);
+            const float tny = fmaf(byte_f(ny, i), ay, bny), tfy = fmaf(byte_f(fy, i), ay, bfy);
+            const float tnz = fmaf(byte_f(nz, i), az, bnz), tfz = fmaf(byte_f(fz, i), az, bfz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            const uint32_t meta = (meta4 >> (8 * i)) & 0xffu;
+            if (tn <= tf) {
+                const uint32_t bits = meta >> 5;
+                const uint32_t pos = meta & 0x1fu;
+                const uint32_t shift = pos >= 24u ? (pos ^ r.octinv) : pos;
+                hitmask |= bits << shift;
+            }
+        }
+    }
+    return hitmask;
+}
+
+}  // namespace rt

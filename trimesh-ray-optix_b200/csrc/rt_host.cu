@@ -1,0 +1,99 @@
+// rt_host.cu — end-to-end entry point with HOST buffers (rt_host_trace_closest).
+//
+// The reference's public call takes CUDA tensors (triro/ray/ray_optix.py:117-146); a caller whose
+// rays live in host memory pays H2D + trace + D2H back to back, the way test/performance_test.py
+// moves its result to the CPU.  This entry point pipelines the three over fixed-size ray chunks on
+// kSlots private streams so the PCIe copies of chunk i+1 / i-1 overlap the traversal of chunk i.
+#include "rt_api.h"
+
+namespace rt {
+constexpr int kSlots = 3;
+constexpr int64_t kHostChunk = 1 << 20;   // rays per chunk
+
+struct SlotLayout {
+    size_t origins, directions, hit, front, tri, loc, uv, scratch, bytes;
+};
+static SlotLayout slot_layout(int64_t chunk) {
+    SlotLayout l;
+    size_t off = 0;
+    auto take = [&](size_t b) { const size_t o = off; off += align_up_sz(b, 256); return o; };
+    l.origins = take((size_t)chunk * 12);
+    l.directions = take((size_t)chunk * 12);
+    l.hit = take((size_t)chunk);
+    l.front = take((size_t)chunk);
+    l.tri = take((size_t)chunk * 4);
+    l.loc = take((size_t)chunk * 12);
+    l.uv = take((size_t)chunk * 8);
+    l.scratch = take(RT_TRACE_SCRATCH_BYTES);
+    l.bytes = off;
+    return l;
+}
+static int64_t chunk_for(int64_t nray) { return nray < kHostChunk ? (nray > 0 ? nray : 1) : kHostChunk; }
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" int rt_host_closest_sizes(int64_t nray, size_t* dev_work_bytes) {
+    RT_REQUIRE(nray >= 0 && dev_work_bytes, RT_ERR_INVALID, "rt_host_closest_sizes: bad arguments");
+    *dev_work_bytes = slot_layout(chunk_for(nray)).bytes * kSlots;
+    return RT_OK;
+}
+
+extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float* h_origins, int origins_broadcast,
+                                     const float* h_directions, uint8_t* h_hit, uint8_t* h_front, int32_t* h_tri_idx,
+                                     float* h_loc, float* h_uv, void* dev_work, size_t dev_work_bytes) {
+    RT_REQUIRE(nray >= 0, RT_ERR_INVALID, "rt_host_trace_closest: negative ray count");
+    if (nray == 0) return RT_OK;
+    RT_REQUIRE(blob && h_origins && h_directions && h_hit && h_front && h_tri_idx && h_loc && h_uv && dev_work,
+               RT_ERR_INVALID, "rt_host_trace_closest: null pointer");
+    RT_REQUIRE(((uintptr_t)dev_work & 255) == 0, RT_ERR_INVALID, "rt_host_trace_closest: dev_work must be 256-byte aligned");
+    const int64_t chunk = chunk_for(nray);
+    const SlotLayout lay = slot_layout(chunk);
+    RT_REQUIRE(dev_work_bytes >= lay.bytes * kSlots, RT_ERR_SIZE, "rt_host_trace_closest: dev_work too small");
+
+    cudaStream_t streams[kSlots];
+    int made = 0;
+    int rc = RT_OK;
+    for (; made < kSlots; ++made) {
+        if (cudaStreamCreateWithFlags(&streams[made], cudaStreamNonBlocking) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: cudaStreamCreate failed");
+            break;
+        }
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>(dev_work);
+    for (int64_t c = 0, first = 0; rc == RT_OK && first < nray; ++c, first += chunk) {
+        const int s = (int)(c % kSlots);
+        uint8_t* w = base + (size_t)s * lay.bytes;
+        const int64_t m = nray - first < chunk ? nray - first : chunk;
+        cudaStream_t st = streams[s];
+        float* d_o = reinterpret_cast<float*>(w + lay.origins);
+        float* d_d = reinterpret_cast<float*>(w + lay.directions);
+        cudaError_t e = cudaSuccess;
+        if (origins_broadcast) e = cudaMemcpyAsync(d_o, h_origins, 12, cudaMemcpyHostToDevice, st);
+        else e = cudaMemcpyAsync(d_o, h_origins + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, h_directions + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        rt_ray_desc rd;
+        rd.nray = m;
+        rd.shape[0] = 1; rd.shape[1] = 1; rd.shape[2] = m; rd.shape[3] = 3;
+        rd.origins = d_o; rd.directions = d_d;
+        rd.o_stride[0] = 0; rd.o_stride[1] = 0; rd.o_stride[2] = origins_broadcast ? 0 : 3; rd.o_stride[3] = 1;
+        rd.d_stride[0] = 0; rd.d_stride[1] = 0; rd.d_stride[2] = 3; rd.d_stride[3] = 1;
+        rc = rt_trace_closest(blob, &rd, w + lay.hit, w + lay.front, reinterpret_cast<int32_t*>(w + lay.tri),
+                              reinterpret_cast<float*>(w + lay.loc), reinterpret_cast<float*>(w + lay.uv),
+                              w + lay.scratch, st);
+        if (rc != RT_OK) break;
+        e = cudaMemcpyAsync(h_hit + first, w + lay.hit, (size_t)m, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_front + first, w + lay.front, (size_t)m, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_tri_idx + first, w + lay.tri, (size_t)m * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_loc + 3 * first, w + lay.loc, (size_t)m * 12, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_uv + 2 * first, w + lay.uv, (size_t)m * 8, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: D2H copy failed: %s", cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < made; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(streams[i]);
+        if (e != cudaSuccess && rc == RT_OK) rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: %s", cudaGetErrorString(e));
+        cudaStreamDestroy(streams[i]);
+    }
+    return rc;
+}

@@ -1,0 +1,346 @@
+// rt_trace.cu — persistent traversal kernels (sm_100a) and the rt_trace_* / rt_allhits_trace /
+// rt_contains_parity / rt_trace_stats entry points.
+//
+// Replaces the five OptiX pipelines of the reference (sbtdef.h:37-42): the launchers
+// intersectsAny/First/Closest/Count/Location (triro/backend/ray.cpp:161-378) and their device
+// programs (triro/backend/shaders.cu:67-246), including the strided ray fetch getRay
+// (shaders.cu:27-63).
+//
+// Execution model: persistent CTAs (grid = SMs x resident CTAs); each warp repeatedly claims
+// 32 consecutive rays from a global counter, one ray per lane; traversal is rt::traverse().
+#include <type_traits>
+#include "rt_api.h"
+#include "rt_traverse.cuh"
+
+namespace rt {
+
+enum TraceMode { kClosest = 0, kFirst = 1, kAny = 2, kCount = 3, kAllHits = 4, kContains = 5 };
+
+constexpr int kTraceThreads = 128;
+
+struct TraceParams {
+    const uint8_t* blob;
+    rt_ray_desc rays;
+    int o_packed, d_packed;      // 1 = row-major contiguous [n,3] -> offset = 3*r
+    float tmax;
+    unsigned long long* ray_counter;
+    // outputs (per mode)
+    uint8_t* hit;
+    uint8_t* front;
+    int32_t* tri;
+    float* loc;
+    float* uv;
+    int32_t* count;
+    // all hits
+    int max_hits;
+    uint4* staging;
+    // contains
+    float dir[3], aabb_lo[3], aabb_hi[3];
+    uint8_t* contain;
+    uint8_t* broken;
+    int32_t* flags;
+    // instrumentation
+    unsigned long long* counters;
+};
+
+struct LocalStack {
+    uint2 e[kMaxDepth];
+    __device__ __forceinline__ void push(int sp, uint32_t x, uint32_t y) { e[sp] = make_uint2(x, y); }
+    __device__ __forceinline__ void pop(int sp, uint32_t& x, uint32_t& y) { const uint2 v = e[sp]; x = v.x; y = v.y; }
+};
+
+__device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int64_t stride[4], int packed, int64_t r) {
+    if (packed) return 3 * r;
+    const int64_t i2 = r % shape[2];
+    const int64_t q = r / shape[2];
+    const int64_t i1 = q % shape[1];
+    const int64_t i0 = q / shape[1];
+    return i0 * stride[0] + i1 * stride[1] + i2 * stride[2];
+}
+
+// records up to max_hits (tri, loc) per ray in traversal order, like the reference's
+// __anyhit__intersectsLocation (shaders.cu:207-224), while counting every hit
+template <class S>
+struct AllHitsVisitor : S {
+    float tmax;
+    int32_t count = 0;
+    int max_hits;
+    uint4* out;
+    const uint8_t* tris;
+    __device__ __forceinline__ AllHitsVisitor(float tmax0, int mh, uint4* o, const uint8_t* t)
+        : tmax(tmax0), max_hits(mh), out(o), tris(t) {}
+    __device__ __forceinline__ bool hit(const Ray&, const TriHit& h, int32_t prim, uint32_t slot) {
+        if (h.t > 0.0f && h.t < tmax) {
+            if (count < max_hits) {
+                const uint8_t* tp = tris + (size_t)slot * 48u;
+                const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
+                const HitAttr at = tri_attr(h, as_float(a.x), as_float(a.y), as_float(a.z), as_float(b.x),
+                                            as_float(b.y), as_float(b.z), as_float(c.x), as_float(c.y), as_float(c.z));
+                out[count] = make_uint4((uint32_t)prim, __float_as_uint(at.lx), __float_as_uint(at.ly),
+                                        __float_as_uint(at.lz));
+            }
+            ++count;
+        }
+        return false;
+    }
+};
+
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ TraceParams p) {
+    using S = typename std::conditional<STATS, Stats, NoStats>::type;
+    const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
+    const uint8_t* tris = p.blob + hdr->tris_offset;
+    const uint8_t* nodes = p.blob + hdr->nodes_offset;
+    const int lane = threadIdx.x & 31;
+    const int64_t nray = p.rays.nray;
+    LocalStack stack;
+    unsigned long long st_nodes = 0, st_tris = 0, st_rays = 0, st_hits = 0;
+    bool any_inside = false, any_broken = false;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.ray_counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= nray) break;
+        const int64_t r = (int64_t)base + lane;
+        if (r < nray) {
+            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_packed, r);
+            const int64_t os = p.rays.o_stride[3];
+            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
+            float dx, dy, dz;
+            if (MODE == kContains) {
+                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+            } else {
+                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_packed, r);
+                const int64_t ds = p.rays.d_stride[3];
+                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+            }
+            Ray ray;
+            ray_setup(ray, ox, oy, oz, dx, dy, dz);
+            if (MODE == kClosest || MODE == kFirst) {
+                ClosestVisitor<S> vis(p.tmax);
+                traverse(nodes, tris, ray, vis, stack);
+                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.prim >= 0; }
+                if (MODE == kFirst) {
+                    if (p.tri) p.tri[r] = vis.prim;
+                } else if (p.hit) {
+                    if (vis.prim >= 0) {
+                        const uint8_t* tp = tris + (size_t)vis.slot * 48u;
+                        const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
+                        const float v0x = as_float(a.x), v0y = as_float(a.y), v0z = as_float(a.z);
+                        const float v1x = as_float(b.x), v1y = as_float(b.y), v1z = as_float(b.z);
+                        const float v2x = as_float(c.x), v2y = as_float(c.y), v2z = as_float(c.z);
+                        TriHit h;
+                        tri_test(ray, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h);
+                        const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+                        p.hit[r] = 1; p.front[r] = tri_front(ray, h) ? 1 : 0; p.tri[r] = vis.prim;
+                        p.loc[3 * r] = at.lx; p.loc[3 * r + 1] = at.ly; p.loc[3 * r + 2] = at.lz;
+                        p.uv[2 * r] = at.uv0; p.uv[2 * r + 1] = at.uv1;
+                    } else {
+                        // reference miss program: shaders.cu:128-135
+                        p.hit[r] = 0; p.front[r] = 0; p.tri[r] = -1;
+                        p.loc[3 * r] = 0.f; p.loc[3 * r + 1] = 0.f; p.loc[3 * r + 2] = 0.f;
+                        p.uv[2 * r] = 0.f; p.uv[2 * r + 1] = 0.f;
+                    }
+                }
+            } else if (MODE == kAny) {
+                AnyVisitor<S> vis(p.tmax);
+                traverse(nodes, tris, ray, vis, stack);
+                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.found; }
+                if (p.hit) p.hit[r] = vis.found ? 1 : 0;
+            } else if (MODE == kCount) {
+                CountVisitor<S> vis(p.tmax);
+                traverse(nodes, tris, ray, vis, stack);
+                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.count > 0; }
+                if (p.count) p.count[r] = vis.count;
+            } else if (MODE == kAllHits) {
+                AllHitsVisitor<S> vis(p.tmax, p.max_hits, p.staging + (size_t)r * p.max_hits, tris);
+                traverse(nodes, tris, ray, vis, stack);
+                p.count[r] = vis.count < p.max_hits ? vis.count : p.max_hits;
+            } else if (MODE == kContains) {
+                // reference: ray_optix.py:238-267
+                const bool inside = ox > p.aabb_lo[0] && oy > p.aabb_lo[1] && oz > p.aabb_lo[2] &&
+                                    ox < p.aabb_hi[0] && oy < p.aabb_hi[1] && oz < p.aabb_hi[2];
+                CountVisitor<S> plus(p.tmax);
+                traverse(nodes, tris, ray, plus, stack);
+                Ray back;
+                ray_setup(back, ox, oy, oz, -dx, -dy, -dz);
+                CountVisitor<S> minus(p.tmax);
+                traverse(nodes, tris, back, minus, stack);
+                const bool agree = (plus.count & 1) && (minus.count & 1);
+                const bool brk = !agree && (plus.count == 0 || minus.count == 0);
+                p.contain[r] = (inside && agree) ? 1 : 0;
+                p.broken[r] = brk ? 1 : 0;
+                any_inside |= inside;
+                any_broken |= brk;
+            }
+        }
+    }
+    if (MODE == kContains) {
+        if (__any_sync(0xffffffffu, any_inside) && lane == 0) atomicOr(&p.flags[0], 1);
+        if (__any_sync(0xffffffffu, any_broken) && lane == 0) atomicOr(&p.flags[1], 1);
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_nodes += __shfl_xor_sync(0xffffffffu, st_nodes, o);
+            st_tris += __shfl_xor_sync(0xffffffffu, st_tris, o);
+            st_rays += __shfl_xor_sync(0xffffffffu, st_rays, o);
+            st_hits += __shfl_xor_sync(0xffffffffu, st_hits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&p.counters[0], st_nodes);
+            atomicAdd(&p.counters[1], st_tris);
+            atomicAdd(&p.counters[2], st_rays);
+            atomicAdd(&p.counters[3], st_hits);
+        }
+    }
+}
+
+static bool is_packed(const int64_t shape[4], const int64_t stride[4]) {
+    // row-major contiguous [s0,s1,s2,3]; dimensions of extent 1 may carry any stride
+    if (stride[3] != 1) return false;
+    int64_t expect = 3;
+    for (int i = 2; i >= 0; --i) {
+        if (shape[i] != 1 && stride[i] != expect) return false;
+        expect *= shape[i];
+    }
+    return true;
+}
+
+static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
+    RT_REQUIRE(rays != nullptr, RT_ERR_INVALID, "%s: null ray descriptor", fn);
+    RT_REQUIRE(rays->nray >= 0, RT_ERR_INVALID, "%s: negative ray count", fn);
+    RT_REQUIRE(rays->shape[3] == 3, RT_ERR_INVALID, "%s: last dimension must be 3 (got %lld)", fn,
+               (long long)rays->shape[3]);
+    RT_REQUIRE(rays->shape[0] >= 0 && rays->shape[1] >= 0 && rays->shape[2] >= 0, RT_ERR_INVALID,
+               "%s: negative shape", fn);
+    RT_REQUIRE(rays->shape[0] * rays->shape[1] * rays->shape[2] == rays->nray, RT_ERR_INVALID,
+               "%s: nray %lld does not match shape", fn, (long long)rays->nray);
+    if (rays->nray > 0) {
+        RT_REQUIRE(rays->origins != nullptr, RT_ERR_INVALID, "%s: null origins", fn);
+        RT_REQUIRE(!need_dirs || rays->directions != nullptr, RT_ERR_INVALID, "%s: null directions", fn);
+    }
+    return RT_OK;
+}
+
+template <int MODE, bool STATS>
+static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray_desc* rays, void* scratch,
+                  cudaStream_t stream) {
+    RT_REQUIRE(blob != nullptr && ((uintptr_t)blob & 15) == 0, RT_ERR_INVALID, "%s: blob null or not 16-byte aligned", fn);
+    RT_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 7) == 0, RT_ERR_INVALID, "%s: scratch null or misaligned", fn);
+    const int rc = check_rays(fn, rays, MODE != kContains);
+    if (rc != RT_OK) return rc;
+    if (rays->nray == 0) return RT_OK;
+    DeviceInfo dev;
+    RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "%s: no CUDA device", fn);
+    p.blob = reinterpret_cast<const uint8_t*>(blob);
+    p.rays = *rays;
+    p.o_packed = is_packed(rays->shape, rays->o_stride) ? 1 : 0;
+    p.d_packed = (MODE != kContains && is_packed(rays->shape, rays->d_stride)) ? 1 : 0;
+    p.tmax = RT_TMAX_DEFAULT;
+    p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
+    RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
+    static thread_local int per_sm_cache[2][8] = {{0}};
+    int& per_sm = per_sm_cache[STATS ? 1 : 0][MODE];
+    if (per_sm == 0) {
+        RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS>, kTraceThreads, 0));
+        RT_REQUIRE(per_sm > 0, RT_ERR_CUDA, "%s: kernel does not fit an SM", fn);
+    }
+    int64_t grid = (int64_t)dev.sm_count * per_sm;
+    const int64_t need = (rays->nray + kTraceThreads - 1) / kTraceThreads;
+    if (grid > need) grid = need;
+    k_trace<MODE, STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" int rt_trace_any(const void* blob, const rt_ray_desc* rays, uint8_t* hit, void* scratch, void* stream) {
+    RT_REQUIRE(hit || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_any: null output");
+    TraceParams p = {};
+    p.hit = hit;
+    return launch<kAny, false>("rt_trace_any", p, blob, rays, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_trace_first(const void* blob, const rt_ray_desc* rays, int32_t* tri_idx, void* scratch, void* stream) {
+    RT_REQUIRE(tri_idx || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_first: null output");
+    TraceParams p = {};
+    p.tri = tri_idx;
+    return launch<kFirst, false>("rt_trace_first", p, blob, rays, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8_t* hit, uint8_t* front,
+                                int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream) {
+    RT_REQUIRE((hit && front && tri_idx && loc && uv) || (rays && rays->nray == 0), RT_ERR_INVALID,
+               "rt_trace_closest: null output");
+    TraceParams p = {};
+    p.hit = hit; p.front = front; p.tri = tri_idx; p.loc = loc; p.uv = uv;
+    return launch<kClosest, false>("rt_trace_closest", p, blob, rays, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream) {
+    RT_REQUIRE(count || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_count: null output");
+    TraceParams p = {};
+    p.count = count;
+    return launch<kCount, false>("rt_trace_count", p, blob, rays, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_contains_parity(const void* blob, const rt_ray_desc* points, const float dir[3],
+                                  const float aabb_lo[3], const float aabb_hi[3], uint8_t* contain, uint8_t* broken,
+                                  int32_t* flags_dev, void* scratch, void* stream) {
+    RT_REQUIRE(dir && aabb_lo && aabb_hi && flags_dev, RT_ERR_INVALID, "rt_contains_parity: null argument");
+    RT_REQUIRE((contain && broken) || (points && points->nray == 0), RT_ERR_INVALID,
+               "rt_contains_parity: null output");
+    TraceParams p = {};
+    for (int a = 0; a < 3; ++a) { p.dir[a] = dir[a]; p.aabb_lo[a] = aabb_lo[a]; p.aabb_hi[a] = aabb_hi[a]; }
+    p.contain = contain; p.broken = broken; p.flags = flags_dev;
+    RT_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
+    return launch<kContains, false>("rt_contains_parity", p, blob, points, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_trace_stats(const void* blob, const rt_ray_desc* rays, int mode, uint64_t* counters_dev,
+                              void* scratch, void* stream) {
+    RT_REQUIRE(counters_dev != nullptr, RT_ERR_INVALID, "rt_trace_stats: null counters");
+    RT_CUDA_TRY(cudaMemsetAsync(counters_dev, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+    TraceParams p = {};
+    p.counters = reinterpret_cast<unsigned long long*>(counters_dev);
+    switch (mode) {
+        case 0: return launch<kClosest, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
+        case 1: return launch<kAny, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
+        case 2: return launch<kCount, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
+        default: return set_error(RT_ERR_INVALID, "rt_trace_stats: mode must be 0 (closest), 1 (any) or 2 (count)");
+    }
+}
+
+// all-hits trace lives here (kernel), its scan + scatter in rt_compact.cu
+namespace rt {
+int scan_counts_i32(const int32_t* counts, int64_t n, void* workspace, size_t workspace_bytes, int64_t* total_dev,
+                    cudaStream_t stream);
+size_t scan_workspace_bytes(int64_t n);
+}
+
+extern "C" int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_bytes, size_t* workspace_bytes) {
+    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE && staging_bytes && workspace_bytes,
+               RT_ERR_INVALID, "rt_allhits_sizes: bad arguments");
+    *staging_bytes = (size_t)nray * (size_t)max_hits * 16u;
+    *workspace_bytes = scan_workspace_bytes(nray);
+    return RT_OK;
+}
+
+extern "C" int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, int32_t* count_clamped,
+                                void* staging, void* workspace, size_t workspace_bytes, int64_t* total_dev,
+                                void* scratch, void* stream) {
+    RT_REQUIRE(max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE, RT_ERR_INVALID, "rt_allhits_trace: max_hits out of range");
+    RT_REQUIRE(total_dev != nullptr, RT_ERR_INVALID, "rt_allhits_trace: null total");
+    RT_REQUIRE((count_clamped && staging && workspace) || (rays && rays->nray == 0), RT_ERR_INVALID,
+               "rt_allhits_trace: null buffer");
+    TraceParams p = {};
+    p.count = count_clamped; p.max_hits = max_hits; p.staging = reinterpret_cast<uint4*>(staging);
+    const int rc = launch<kAllHits, false>("rt_allhits_trace", p, blob, rays, scratch, (cudaStream_t)stream);
+    if (rc != RT_OK) return rc;
+    return scan_counts_i32(count_clamped, rays->nray, workspace, workspace_bytes, total_dev, (cudaStream_t)stream);
+}

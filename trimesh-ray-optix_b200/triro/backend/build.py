@@ -1,0 +1,77 @@
+"""Builds libtriro_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+Replaces the reference's two-stage build: `nvcc -optix-ir` of shaders.cu at install time
+(setup.py:27-39) plus the JIT compile of base.cpp/binding.cpp/ray.cpp at first import
+(triro/backend/ops.py:24-45).  Here there is one ahead-of-time build and no OptiX SDK.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.normpath(os.path.join(HERE, "..", "..", "csrc"))
+INCLUDE = os.path.normpath(os.path.join(HERE, "..", "..", "..", "include"))
+LIB_PATH = os.path.join(HERE, "libtriro_b200.so")
+UNITS = ["rt_build.cu", "rt_trace.cu", "rt_compact.cu", "rt_host.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (looked at $NVCC, /usr/local/cuda/bin/nvcc, PATH)")
+
+
+def sources() -> list[str]:
+    out = [os.path.join(CSRC, u) for u in UNITS]
+    out += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    out.append(os.path.join(INCLUDE, "raymesh_b200.h"))
+    return out
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit (in parallel) and link the shared library."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = nvcc_path()
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(unit: str) -> str:
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, unit), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {unit}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
+    tmp = LIB_PATH + ".tmp"
+    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", tmp, *objs], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,472 @@
+"""Operator layer over the C ABI of libtriro_b200.so (include/raymesh_b200.h).
+
+Drop-in for the reference's op shim `triro/backend/ops.py:12-192`: same function names and
+argument meaning (`intersects_any/first/closest/count/location(accel, origins, dirs)`,
+`get_module()`, the five init functions called at import), but instead of JIT-compiling a
+pybind11/OptiX module it loads a prebuilt CUDA library through ctypes.  torch only provides
+device memory and the stream; every computation is a hand-written sm_100a kernel.
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present the
+functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+from typing import Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libtriro_b200.so"
+MAX_ANYHIT_SIZE = 8          # reference LaunchParams.h:8
+MAX_BATCH_DIMS = 3           # reference LaunchParams.h:9 (MAX_SIZE_LENGTH = 4 incl. the trailing 3)
+TRACE_SCRATCH_BYTES = 256
+BLOB_HEADER_BYTES = 256
+BLOB_MAGIC = 0x38485642
+MAX_DEPTH = 60               # rt_core.cuh kMaxDepth
+HOST_CHUNK = 1 << 20
+
+_lib = None
+
+
+class RayDesc(C.Structure):
+    """rt_ray_desc — mirrors RayInput (reference LaunchParams.h:11-28)."""
+
+    _fields_ = [
+        ("nray", C.c_int64),
+        ("shape", C.c_int64 * 4),
+        ("origins", C.c_void_p),
+        ("o_stride", C.c_int64 * 4),
+        ("directions", C.c_void_p),
+        ("d_stride", C.c_int64 * 4),
+    ]
+
+
+def _declare(lib):
+    vp, i64, sz, ci = C.c_void_p, C.c_int64, C.c_size_t, C.c_int
+    psz = C.POINTER(C.c_size_t)
+    prd = C.POINTER(RayDesc)
+    sig = {
+        "rt_last_error": (C.c_char_p, []),
+        "rt_abi_version": (ci, []),
+        "rt_device_sm_count": (ci, []),
+        "rt_bvh_sizes": (ci, [i64, i64, psz, psz]),
+        "rt_bvh_build": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
+        "rt_sort_sizes": (ci, [i64, psz]),
+        "rt_sort_pairs_u64": (ci, [vp, vp, i64, vp, sz, vp]),
+        "rt_trace_any": (ci, [vp, prd, vp, vp, vp]),
+        "rt_trace_first": (ci, [vp, prd, vp, vp, vp]),
+        "rt_trace_closest": (ci, [vp, prd, vp, vp, vp, vp, vp, vp, vp]),
+        "rt_trace_count": (ci, [vp, prd, vp, vp, vp]),
+        "rt_compact_sizes": (ci, [i64, psz]),
+        "rt_compact_scan": (ci, [vp, i64, vp, sz, vp, vp]),
+        "rt_compact_scatter": (ci, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "rt_allhits_sizes": (ci, [i64, ci, psz, psz]),
+        "rt_allhits_trace": (ci, [vp, prd, ci, vp, vp, vp, sz, vp, vp, vp]),
+        "rt_allhits_scatter": (ci, [i64, ci, vp, vp, vp, vp, vp, vp, vp]),
+        "rt_contains_parity": (ci, [vp, prd, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
+                                    vp, vp, vp]),
+        "rt_trace_stats": (ci, [vp, prd, ci, vp, vp, vp]),
+        "rt_host_closest_sizes": (ci, [i64, psz]),
+        "rt_host_trace_closest": (ci, [vp, i64, vp, ci, vp, vp, vp, vp, vp, vp, vp, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTS = None
+
+
+def get_module():
+    """Load libtriro_b200.so (reference: get_module(), ops.py:12-46, which JIT-builds instead)."""
+    global _lib, EXPORTS
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("TRIRO_B200_LIB", os.path.join(_HERE, LIB_NAME))
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    EXPORTS = _declare(lib)
+    if lib.rt_abi_version() != 1:
+        raise RuntimeError(f"{path}: ABI version {lib.rt_abi_version()} != 1")
+    _lib = lib
+    return _lib
+
+
+# The reference initialises OptiX at import (triro/ray/__init__.py:17-22).  There is no OptiX
+# here; the five entry points are kept so that code calling them keeps working.  They make sure
+# the native library is loadable, which is the equivalent "import = ready" guarantee.
+def init_optix():
+    get_module()
+
+
+def create_optix_context():
+    get_module()
+
+
+def create_optix_module():
+    get_module()
+
+
+def create_optix_pipelines():
+    get_module()
+
+
+def build_sbts():
+    get_module()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = get_module().rt_last_error().decode("utf-8", "replace")
+        if rc in (-1, -3):
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: {msg} (status {rc})")
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _scratch(device) -> torch.Tensor:
+    return torch.empty(TRACE_SCRATCH_BYTES, dtype=torch.uint8, device=device)
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def tensor_input_check(*ts: torch.Tensor):
+    """Reference tensorInputCheck (ray.cpp:104-123) checks is_cuda + strided layout and, on
+    failure, prints to stderr and returns an empty tensor; here the same conditions (plus the
+    dtype the reference silently reinterprets) raise ValueError."""
+    for t in ts:
+        if not isinstance(t, torch.Tensor):
+            raise ValueError("input must be a torch.Tensor")
+        if not t.is_cuda:
+            raise ValueError("input tensors must reside in cuda device.")
+        if t.layout != torch.strided:
+            raise ValueError("input tensor layout must be torch.strided.")
+        if t.dtype != torch.float32:
+            raise ValueError(f"input tensors must be float32 (got {t.dtype})")
+
+
+def make_ray_desc(origins: torch.Tensor, dirs: torch.Tensor | None) -> Tuple[RayDesc, tuple]:
+    """fillArray of the reference (ray.cpp:151-159): right-align shape/strides into 4 slots.
+    The batch shape is that of `origins` (ray.cpp:177-179)."""
+    if origins.dim() < 1 or origins.shape[-1] != 3:
+        raise ValueError(f"origins must have shape [*b, 3], got {tuple(origins.shape)}")
+    if dirs is not None and tuple(dirs.shape) != tuple(origins.shape):
+        raise ValueError(f"directions {tuple(dirs.shape)} must have the shape of origins {tuple(origins.shape)}")
+    if dirs is not None and dirs.device != origins.device:
+        raise ValueError("origins and directions must be on the same device")
+    batch = tuple(origins.shape[:-1])
+    if len(batch) > MAX_BATCH_DIMS:
+        raise ValueError(f"at most {MAX_BATCH_DIMS} batch dimensions are supported (reference MAX_SIZE_LENGTH=4)")
+    rd = RayDesc()
+    n = 1
+    for s in batch:
+        n *= s
+    rd.nray = n
+    pad = 4 - origins.dim()
+    for i in range(4):
+        j = i - pad
+        rd.shape[i] = origins.shape[j] if j >= 0 else 1
+        rd.o_stride[i] = origins.stride(j) if j >= 0 else 0
+        rd.d_stride[i] = (dirs.stride(j) if j >= 0 else 0) if dirs is not None else 0
+    rd.origins = origins.data_ptr()
+    rd.directions = dirs.data_ptr() if dirs is not None else None
+    return rd, batch
+
+
+class AccelStructure:
+    """Flat, relocatable BVH8 blob owned by torch (reference: OptixAccelStructureWrapperCPP,
+    ray.h:11-16, whose GAS is an opaque buffer owned by C++)."""
+
+    def __init__(self):
+        self.blob: torch.Tensor | None = None
+        self.header: dict | None = None
+        self.build_ms: float | None = None
+
+    def build(self, vertices: torch.Tensor, faces: torch.Tensor, timing: bool = False):
+        lib = get_module()
+        if not (vertices.is_cuda and faces.is_cuda):
+            raise ValueError("vertices and faces must reside in cuda device.")
+        if vertices.dtype != torch.float32 or faces.dtype != torch.int32:
+            raise ValueError("vertices must be float32 and faces int32")
+        if vertices.dim() != 2 or vertices.shape[1] != 3 or faces.dim() != 2 or faces.shape[1] != 3:
+            raise ValueError("vertices must be [n,3] and faces [f,3]")
+        vertices = vertices.contiguous()
+        faces = faces.contiguous()
+        dev = vertices.device
+        nv, nf = vertices.shape[0], faces.shape[0]
+        ws_b, blob_b = C.c_size_t(), C.c_size_t()
+        _check(lib.rt_bvh_sizes(nv, nf, C.byref(ws_b), C.byref(blob_b)), "rt_bvh_sizes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+            blob = torch.empty(blob_b.value, dtype=torch.uint8, device=dev)
+            if timing:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _check(lib.rt_bvh_build(_ptr(vertices), nv, _ptr(faces), nf, _ptr(ws), ws_b.value, _ptr(blob),
+                                    blob_b.value, _stream(dev)), "rt_bvh_build")
+            if timing:
+                e1.record()
+            # the reference's build is synchronous too (2x cudaDeviceSynchronize, ray.cpp:85,95)
+            hdr = parse_header(blob[:BLOB_HEADER_BYTES].cpu().numpy().tobytes())
+            if timing:
+                self.build_ms = e0.elapsed_time(e1)
+        del ws
+        if hdr["magic"] != BLOB_MAGIC:
+            raise RuntimeError("rt_bvh_build produced an invalid blob header")
+        if hdr["bad_index_faces"]:
+            raise ValueError(f"{hdr['bad_index_faces']} faces reference vertices outside [0, {nv})")
+        if hdr["node_overflow"]:
+            raise RuntimeError("BVH node pool overflow (internal error)")
+        if hdr["depth"] > MAX_DEPTH:
+            raise RuntimeError(f"BVH depth {hdr['depth']} exceeds the traversal stack ({MAX_DEPTH}); mesh too degenerate")
+        self.blob = blob
+        self.header = hdr
+        return self
+
+    def adopt(self, blob: torch.Tensor):
+        """Attach to a blob received from elsewhere (NCCL broadcast, torch.load)."""
+        hdr = parse_header(blob[:BLOB_HEADER_BYTES].cpu().numpy().tobytes())
+        if hdr["magic"] != BLOB_MAGIC or hdr["abi_version"] != 1:
+            raise ValueError("not a BVH blob of this ABI version")
+        self.blob = blob
+        self.header = hdr
+        return self
+
+    def used(self) -> torch.Tensor:
+        """Prefix of the blob that must travel (header + triangles + nodes in use)."""
+        return self.blob[: self.header["used_bytes"]]
+
+    def free(self):
+        self.blob = None
+        self.header = None
+
+
+def parse_header(raw: bytes) -> dict:
+    magic, abi, n_tris, n_nodes, depth, cap = struct.unpack_from("<6I", raw, 0)
+    tris_off, nodes_off, used = struct.unpack_from("<3Q", raw, 24)
+    aabb = struct.unpack_from("<6f", raw, 48)
+    bad, overflow = struct.unpack_from("<2I", raw, 72)
+    return dict(magic=magic, abi_version=abi, n_tris=n_tris, n_nodes=n_nodes, depth=depth, n_nodes_cap=cap,
+                tris_offset=tris_off, nodes_offset=nodes_off, used_bytes=used, aabb_lo=aabb[:3], aabb_hi=aabb[3:],
+                bad_index_faces=bad, node_overflow=overflow)
+
+
+def _blob_of(accel) -> torch.Tensor:
+    inner = getattr(accel, "_inner", accel)
+    if inner.blob is None:
+        raise RuntimeError("acceleration structure has not been built")
+    return inner.blob
+
+
+# ------------------------------------------------------------------ operators (reference ops.py:84-192)
+def intersects_any(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """Bool[*b]: does each ray hit anything with 0 < t < 1e7 (reference ops.py:84-101)."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    rd, batch = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty(batch, dtype=torch.bool, device=dev)
+        _check(get_module().rt_trace_any(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
+               "rt_trace_any")
+    return out
+
+
+def intersects_first(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """Int32[*b]: index of the nearest hit triangle or -1 (reference ops.py:104-119)."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    rd, batch = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty(batch, dtype=torch.int32, device=dev)
+        _check(get_module().rt_trace_first(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
+               "rt_trace_first")
+    return out
+
+
+def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tensor):
+    """(hit Bool[*b], front Bool[*b], tri Int32[*b], loc Float32[*b,3], uv Float32[*b,2])
+    (reference ops.py:122-149, ray.cpp:231-289)."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    rd, batch = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        hit = torch.empty(batch, dtype=torch.bool, device=dev)
+        front = torch.empty(batch, dtype=torch.bool, device=dev)
+        tri = torch.empty(batch, dtype=torch.int32, device=dev)
+        loc = torch.empty((*batch, 3), dtype=torch.float32, device=dev)
+        uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
+        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc),
+                                             _ptr(uv), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest")
+    return hit, front, tri, loc, uv
+
+
+def compact_closest(hit, front, tri, loc, uv):
+    """Order-preserving stream compaction of dense closest-hit results: returns
+    (front[h], ray_idx[h] int32, tri[h], loc[h,3], uv[h,2]) — what the reference computes with
+    arange + five boolean-mask gathers (ray_optix.py:142-144)."""
+    lib = get_module()
+    dev = hit.device
+    n = hit.numel()
+    with torch.cuda.device(dev):
+        ws_b = C.c_size_t()
+        _check(lib.rt_compact_sizes(n, C.byref(ws_b)), "rt_compact_sizes")
+        ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        _check(lib.rt_compact_scan(_ptr(hit), n, _ptr(ws), ws.numel(), _ptr(total), _stream(dev)), "rt_compact_scan")
+        h = int(total.item())   # the one host sync the API needs: output sizes
+        front_c = torch.empty(h, dtype=torch.bool, device=dev)
+        ray_idx = torch.empty(h, dtype=torch.int32, device=dev)
+        tri_c = torch.empty(h, dtype=torch.int32, device=dev)
+        loc_c = torch.empty((h, 3), dtype=torch.float32, device=dev)
+        uv_c = torch.empty((h, 2), dtype=torch.float32, device=dev)
+        if h > 0:
+            _check(lib.rt_compact_scatter(_ptr(hit), n, _ptr(ws), _ptr(front), _ptr(tri), _ptr(loc), _ptr(uv),
+                                          _ptr(front_c), _ptr(ray_idx), _ptr(tri_c), _ptr(loc_c), _ptr(uv_c),
+                                          _stream(dev)), "rt_compact_scatter")
+    return front_c, ray_idx, tri_c, loc_c, uv_c
+
+
+def intersects_count(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """Int32[*b]: number of triangles hit with 0 < t < 1e7 (reference ops.py:152-168)."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    rd, batch = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty(batch, dtype=torch.int32, device=dev)
+        _check(get_module().rt_trace_count(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
+               "rt_trace_count")
+    return out
+
+
+def intersects_location(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = MAX_ANYHIT_SIZE):
+    """(loc Float32[h,3], ray_idx Int32[h], tri_idx Int32[h]): up to 8 hits per ray, grouped by
+    ray in ascending ray order (reference ops.py:171-192, ray.cpp:324-378) — one traversal
+    instead of the reference's two."""
+    tensor_input_check(origins, dirs)
+    lib = get_module()
+    blob = _blob_of(accel_structure)
+    rd, _ = make_ray_desc(origins, dirs)
+    dev = origins.device
+    n = rd.nray
+    with torch.cuda.device(dev):
+        st_b, ws_b = C.c_size_t(), C.c_size_t()
+        _check(lib.rt_allhits_sizes(n, max_hits, C.byref(st_b), C.byref(ws_b)), "rt_allhits_sizes")
+        staging = torch.empty(max(st_b.value, 16), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
+        counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        _check(lib.rt_allhits_trace(_ptr(blob), C.byref(rd), max_hits, _ptr(counts), _ptr(staging), _ptr(ws), ws.numel(),
+                                    _ptr(total), _ptr(_scratch(dev)), _stream(dev)), "rt_allhits_trace")
+        h = int(total.item())
+        loc = torch.empty((h, 3), dtype=torch.float32, device=dev)
+        ray_idx = torch.empty(h, dtype=torch.int32, device=dev)
+        tri_idx = torch.empty(h, dtype=torch.int32, device=dev)
+        if h > 0:
+            _check(lib.rt_allhits_scatter(n, max_hits, _ptr(counts), _ptr(staging), _ptr(ws), _ptr(loc), _ptr(ray_idx),
+                                          _ptr(tri_idx), _stream(dev)), "rt_allhits_scatter")
+    return loc, ray_idx, tri_idx
+
+
+def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, aabb_hi):
+    """Fused core of contains_points (reference ray_optix.py:238-267): returns
+    (contain Bool[*b], broken Bool[*b], flags Int32[2] = [any(inside_aabb), any(broken)])."""
+    tensor_input_check(points)
+    blob = _blob_of(accel_structure)
+    rd, batch = make_ray_desc(points, None)
+    dev = points.device
+    d3 = (C.c_float * 3)(*[float(x) for x in direction])
+    lo3 = (C.c_float * 3)(*[float(x) for x in aabb_lo])
+    hi3 = (C.c_float * 3)(*[float(x) for x in aabb_hi])
+    with torch.cuda.device(dev):
+        contain = torch.empty(batch, dtype=torch.bool, device=dev)
+        broken = torch.empty(batch, dtype=torch.bool, device=dev)
+        flags = torch.empty(2, dtype=torch.int32, device=dev)
+        _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), d3, lo3, hi3, _ptr(contain), _ptr(broken),
+                                               _ptr(flags), _ptr(_scratch(dev)), _stream(dev)), "rt_contains_parity")
+    return contain, broken, flags
+
+
+def trace_stats(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, mode: str = "closest") -> dict:
+    """Instrumented traversal: mean BVH8 nodes / triangles fetched per ray (roofline input)."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    rd, _ = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        _check(get_module().rt_trace_stats(_ptr(blob), C.byref(rd), {"closest": 0, "any": 1, "count": 2}[mode],
+                                           _ptr(counters), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_stats")
+        c = counters.cpu().tolist()
+    rays = max(c[2], 1)
+    return dict(nodes=c[0], tris=c[1], rays=c[2], hits=c[3], nodes_per_ray=c[0] / rays, tris_per_ray=c[1] / rays,
+                hit_fraction=c[3] / rays)
+
+
+def host_closest(accel_structure, origins_host: torch.Tensor, dirs_host: torch.Tensor, out: dict | None = None,
+                 work: torch.Tensor | None = None):
+    """End-to-end closest hit with HOST (ideally pinned) buffers: rt_host_trace_closest pipelines
+    H2D copy, traversal and D2H copy over ray chunks.  origins_host may be [n,3] or a single
+    [3]/[1,3] origin shared by all rays.  Returns a dict of host tensors."""
+    lib = get_module()
+    blob = _blob_of(accel_structure)
+    dev = blob.device
+    d = dirs_host
+    if d.is_cuda or d.dtype != torch.float32 or not d.is_contiguous() or d.shape[-1] != 3:
+        raise ValueError("dirs_host must be a contiguous float32 host tensor [*b,3]")
+    n = d.numel() // 3
+    o = origins_host
+    if o.is_cuda or o.dtype != torch.float32 or not o.is_contiguous():
+        raise ValueError("origins_host must be a contiguous float32 host tensor")
+    bcast = 1 if o.numel() == 3 else 0
+    if not bcast and o.numel() != 3 * n:
+        raise ValueError("origins_host must hold 3 or 3*nray floats")
+    batch = tuple(d.shape[:-1])
+    if out is None:
+        pin = torch.cuda.is_available()
+        out = dict(hit=torch.empty(batch, dtype=torch.bool, pin_memory=pin),
+                   front=torch.empty(batch, dtype=torch.bool, pin_memory=pin),
+                   tri=torch.empty(batch, dtype=torch.int32, pin_memory=pin),
+                   loc=torch.empty((*batch, 3), dtype=torch.float32, pin_memory=pin),
+                   uv=torch.empty((*batch, 2), dtype=torch.float32, pin_memory=pin))
+    with torch.cuda.device(dev):
+        wb = C.c_size_t()
+        _check(lib.rt_host_closest_sizes(n, C.byref(wb)), "rt_host_closest_sizes")
+        if work is None or work.numel() < wb.value:
+            work = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+        torch.cuda.current_stream(dev).synchronize()   # blob must be complete before the private streams read it
+        _check(lib.rt_host_trace_closest(_ptr(blob), n, C.c_void_p(o.data_ptr()), bcast, C.c_void_p(d.data_ptr()),
+                                         C.c_void_p(out["hit"].data_ptr()), C.c_void_p(out["front"].data_ptr()),
+                                         C.c_void_p(out["tri"].data_ptr()), C.c_void_p(out["loc"].data_ptr()),
+                                         C.c_void_p(out["uv"].data_ptr()), _ptr(work), work.numel()),
+               "rt_host_trace_closest")
+    return out
+
+
+def sort_pairs_u64(keys: torch.Tensor, vals: torch.Tensor):
+    """In-place onesweep radix sort of (uint64 keys as int64 storage, int32 values) — exposed for tests."""
+    lib = get_module()
+    dev = keys.device
+    n = keys.numel()
+    with torch.cuda.device(dev):
+        wb = C.c_size_t()
+        _check(lib.rt_sort_sizes(n, C.byref(wb)), "rt_sort_sizes")
+        ws = torch.empty(max(wb.value, 256), dtype=torch.uint8, device=dev)
+        _check(lib.rt_sort_pairs_u64(_ptr(keys), _ptr(vals), n, _ptr(ws), ws.numel(), _stream(dev)), "rt_sort_pairs_u64")
+    return keys, vals
