@@ -1,0 +1,197 @@
+"""Ray-slice data parallelism over several GPUs (one process per GPU, torch.distributed).
+
+The reference is single-GPU (one global OptiX context, triro/backend/base.cpp:33-41); this
+layer is what BASELINE.json's north_star adds: the mesh/BVH is built once on `src` and
+broadcast as one flat blob over NCCL (NVLink 5 / NVSwitch), every rank traces a contiguous
+slice of the flattened ray index space, and results are either kept sharded or gathered —
+variable-length all-hit / compacted results included, with ray indices rebased to the global
+numbering so that the concatenation equals the single-GPU answer.
+
+There is no compute/collective fusion here on purpose: the path has no exchange step between
+kernels (rays are independent), the only collectives are one broadcast per build and an
+optional gather of results.
+
+The collective plumbing is backend-agnostic (works with gloo on CPU tensors), which is how the
+host logic is tested without GPUs (tests/test_distributed_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of n rays owned by `rank`: ceil(n / world) rays per rank."""
+    per = (n + world - 1) // world if world > 0 else n
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def slice_rays(origins: torch.Tensor, directions: torch.Tensor, lo: int, hi: int):
+    """Slice the FLATTENED batch index space [lo, hi) of [*b, 3] tensors without copying when the
+    batch is one-dimensional; strided / broadcast multi-dimensional inputs are flattened by index
+    (reshape copies only what it must)."""
+    o = origins.reshape(-1, 3) if origins.dim() != 2 else origins
+    d = directions.reshape(-1, 3) if directions.dim() != 2 else directions
+    return o[lo:hi], d[lo:hi]
+
+
+def broadcast_blob(blob: torch.Tensor | None, src: int = 0, group=None, device=None) -> torch.Tensor:
+    """Broadcast the used prefix of a BVH blob from `src` to every rank (ncclBroadcast)."""
+    rank = dist.get_rank(group)
+    size = torch.zeros(1, dtype=torch.int64, device=device if device is not None else (blob.device if blob is not None else "cpu"))
+    if rank == src:
+        size[0] = blob.numel()
+    dist.broadcast(size, src=src, group=group)
+    n = int(size.item())
+    if rank != src:
+        blob = torch.empty(n, dtype=torch.uint8, device=size.device)
+    dist.broadcast(blob, src=src, group=group)
+    return blob
+
+
+def gather_fixed(x: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """Concatenate per-rank tensors whose leading dimension is counts[rank] (ranks in order).
+    Uses a padded all_gather (every rank contributes max(counts) rows)."""
+    world = dist.get_world_size(group)
+    m = max(counts) if len(counts) else 0
+    if m == 0:
+        return x[:0]
+    pad = torch.zeros((m, *x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[: x.shape[0]] = x
+    if pad.dtype == torch.bool:
+        bufs = [torch.empty_like(pad, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(bufs, pad.to(torch.uint8), group=group)
+        bufs = [b.to(torch.bool) for b in bufs]
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def all_counts(n_local: int, device, group=None) -> List[int]:
+    """all_gather of one int64 per rank (per-rank hit totals)."""
+    world = dist.get_world_size(group)
+    t = torch.tensor([n_local], dtype=torch.int64, device=device)
+    bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(bufs, t, group=group)
+    return [int(b.item()) for b in bufs]
+
+
+class ShardedRayMeshIntersector:
+    """Wraps a per-rank intersector (anything with the RayMeshIntersector query methods).
+
+    Every method takes the FULL ray batch (replicated on all ranks, or at least the rank's own
+    slice valid) and traces only this rank's slice.  With gather=True every rank returns the
+    full result, identical to a single-GPU call; with gather=False it returns its slice plus the
+    slice bounds.
+    """
+
+    def __init__(self, local, group=None):
+        self.local = local
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    # -- construction ------------------------------------------------------------
+    @classmethod
+    def build(cls, vertices: torch.Tensor, faces: torch.Tensor, src: int = 0, group=None):
+        """Build the BVH on `src`, broadcast the blob, attach it on every rank."""
+        from triro.ray.ray_optix import OptixAccelStructureWrapper, RayMeshIntersector
+
+        rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if rank == src:
+            local = RayMeshIntersector(vertices=vertices, faces=faces)
+            blob = broadcast_blob(local.as_wrapper._inner.used().contiguous(), src, group, dev)
+        else:
+            blob = broadcast_blob(None, src, group, dev)
+            local = RayMeshIntersector.__new__(RayMeshIntersector)
+            local.as_wrapper = OptixAccelStructureWrapper()
+            local.as_wrapper._inner.adopt(blob)
+            local.mesh_vertices = None
+            local.mesh_faces = None
+        # mesh AABB over all vertices is needed by contains_points: broadcast 6 floats
+        aabb = torch.zeros(6, dtype=torch.float32, device=dev)
+        if rank == src:
+            aabb[:3] = local.mesh_aabb[0]; aabb[3:] = local.mesh_aabb[1]
+        dist.broadcast(aabb, src=src, group=group)
+        if rank != src:
+            local.mesh_aabb = (aabb[:3].clone(), aabb[3:].clone())
+            local._aabb_host = (aabb[:3].tolist(), aabb[3:].tolist())
+        return cls(local, group)
+
+    # -- helpers -----------------------------------------------------------------
+    def _slice(self, origins, directions):
+        n = origins.numel() // 3
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        o, d = slice_rays(origins, directions, lo, hi)
+        return n, lo, hi, o, d
+
+    def _counts(self, n):
+        return [shard_bounds(n, self.world, r)[1] - shard_bounds(n, self.world, r)[0] for r in range(self.world)]
+
+    def _dense(self, fn: Callable, origins, directions, gather: bool):
+        batch = tuple(origins.shape[:-1])
+        n, lo, hi, o, d = self._slice(origins, directions)
+        res = fn(o, d)
+        single = not isinstance(res, tuple)
+        res = (res,) if single else res
+        if not gather:
+            return (res[0] if single else res), (lo, hi)
+        counts = self._counts(n)
+        full = tuple(gather_fixed(x, counts, self.group).reshape(*batch, *x.shape[1:]) for x in res)
+        return full[0] if single else full
+
+    # -- queries -----------------------------------------------------------------
+    def intersects_any(self, origins, directions, gather: bool = True):
+        return self._dense(self.local.intersects_any, origins, directions, gather)
+
+    def intersects_first(self, origins, directions, gather: bool = True):
+        return self._dense(self.local.intersects_first, origins, directions, gather)
+
+    def intersects_count(self, origins, directions, gather: bool = True):
+        return self._dense(self.local.intersects_count, origins, directions, gather)
+
+    def intersects_closest(self, origins, directions, stream_compaction: bool = False, gather: bool = True):
+        if not stream_compaction:
+            return self._dense(lambda o, d: self.local.intersects_closest(o, d), origins, directions, gather)
+        batch = tuple(origins.shape[:-1])
+        n, lo, hi, o, d = self._slice(origins, directions)
+        hit, front, ray_idx, tri_idx, loc, uv = self.local.intersects_closest(o, d, stream_compaction=True)
+        ray_idx = ray_idx + lo                                   # rebase to the global ray numbering
+        if not gather:
+            return (hit, front, ray_idx, tri_idx, loc, uv), (lo, hi)
+        hit_full = gather_fixed(hit, self._counts(n), self.group).reshape(batch)
+        hc = all_counts(front.shape[0], front.device, self.group)
+        return (hit_full, gather_fixed(front, hc, self.group), gather_fixed(ray_idx, hc, self.group),
+                gather_fixed(tri_idx, hc, self.group), gather_fixed(loc, hc, self.group), gather_fixed(uv, hc, self.group))
+
+    def intersects_location(self, origins, directions, gather: bool = True):
+        n, lo, hi, o, d = self._slice(origins, directions)
+        loc, ray_idx, tri_idx = self.local.intersects_location(o, d)
+        ray_idx = ray_idx + lo
+        if not gather:
+            return (loc, ray_idx, tri_idx), (lo, hi)
+        hc = all_counts(loc.shape[0], loc.device, self.group)
+        return gather_fixed(loc, hc, self.group), gather_fixed(ray_idx, hc, self.group), gather_fixed(tri_idx, hc, self.group)
+
+    def intersects_id(self, origins, directions, return_locations: bool = False, multiple_hits: bool = True,
+                      gather: bool = True):
+        if multiple_hits:
+            loc, ray_idx, tri_idx = self.intersects_location(origins, directions, gather=True)
+        else:
+            _, _, ray_idx, tri_idx, loc, _ = self.intersects_closest(origins, directions, stream_compaction=True, gather=True)
+        return (tri_idx, ray_idx, loc) if return_locations else (tri_idx, ray_idx)
+
+    def contains_points(self, points, check_direction=None, gather: bool = True):
+        n = points.numel() // 3
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        p = points.reshape(-1, 3)[lo:hi]
+        res = self.local.contains_points(p, check_direction)
+        if not gather:
+            return res, (lo, hi)
+        return gather_fixed(res, self._counts(n), self.group).reshape(points.shape[:-1])
