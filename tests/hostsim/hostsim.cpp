@@ -56,7 +56,6 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     h.tris_offset = lay.tris_offset; h.nodes_offset = lay.nodes_offset;
     if (n == 0) {
         Node8 nd; memset(&nd, 0, sizeof(nd)); nd.ex = nd.ey = nd.ez = 1;
-        for (int s = 0; s < 8; ++s) nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
         memcpy(blob + lay.nodes_offset, &nd, 80);
         h.n_nodes = 1; h.depth = 1; h.used_bytes = lay.nodes_offset + 80;
         memcpy(blob, &h, sizeof(h));
@@ -196,20 +195,19 @@ struct Checker {
         const float sx = exp2_biased(nd.ex), sy = exp2_biased(nd.ey), sz = exp2_biased(nd.ez);
         uint32_t rel = 0;
         for (int s = 0; s < 8; ++s) {
-            const uint32_t meta = nd.meta[s];
-            if (meta == 0) { if (nd.imask & (1u << s)) error = 4; continue; }
+            const bool inner = (nd.imask >> s) & 1u;
+            const uint32_t un = (nd.trimask >> (3 * s)) & 7u;
+            if (!inner && un == 0) continue;
             ++children;
             BBox cb;
-            const bool inner = (meta & 0x1fu) >= 24u;
             if (inner) {
-                if ((meta >> 5) != 1u || (meta & 0x1fu) != 24u + (uint32_t)s || !(nd.imask & (1u << s))) error = 5;
+                if (un != 0) error = 5;
                 cb = walk(nd.child_base + rel, depth + 1);
                 ++rel;
             } else {
-                if (nd.imask & (1u << s)) error = 6;
-                const uint32_t un = meta >> 5, off = meta & 0x1fu;
                 const uint32_t cnt = un == 1 ? 1 : (un == 3 ? 2 : (un == 7 ? 3 : 0));
-                if (cnt == 0 || off + cnt > 24) { error = 7; continue; }
+                if (cnt == 0) { error = 7; continue; }
+                const uint32_t off = (uint32_t)__builtin_popcount(nd.trimask & ((1u << (3 * s)) - 1u));
                 cb.lx = cb.ly = cb.lz = INFINITY; cb.hx = cb.hy = cb.hz = -INFINITY; cb.pad0 = cb.pad1 = 0;
                 for (uint32_t j = 0; j < cnt; ++j) {
                     const uint32_t ti = nd.tri_base + off + j;

@@ -270,8 +270,7 @@ __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n,
         // empty mesh: a root without children, every ray misses
         Node8 nd;
         memset(&nd, 0, sizeof(nd));
-        nd.ex = nd.ey = nd.ez = 1;
-        for (int s = 0; s < 8; ++s) { nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; }
+        nd.ex = nd.ey = nd.ez = 1;   // imask = trimask = 0: no slot is ever reported
         *reinterpret_cast<Node8*>(reinterpret_cast<uint8_t*>(hdr) + lay.nodes_offset) = nd;
     }
 }

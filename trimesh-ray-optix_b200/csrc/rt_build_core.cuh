@@ -257,11 +257,10 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2];
     nd.child_base = child_base;
     nd.tri_base = tri_base;
-    uint32_t imask = 0, rel = 0, toff = 0;
+    uint32_t imask = 0, trimask = 0, rel = 0, toff = 0;
     for (int s = 0; s < 8; ++s) {
         const int i = child_in_slot[s];
         if (i < 0) {
-            nd.meta[s] = 0;
             nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;   // inverted box: never hit
             nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
             continue;
@@ -285,13 +284,12 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
         nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
         if (inner[i]) {
             imask |= 1u << s;
-            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             if (child_base + rel < o.node_cap) o.wide_src[child_base + rel] = ref[i];
             ++rel;
         } else {
             const uint32_t cnt = bt_count(t, ref[i]);
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
-            nd.meta[s] = (uint8_t)((unary << 5) | toff);
+            trimask |= unary << (3 * s);
             const uint32_t f0 = bt_first(t, ref[i]);
             for (uint32_t j = 0; j < cnt; ++j) {
                 const uint32_t prim = t.sorted_prim[f0 + j];
@@ -309,6 +307,8 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
         }
     }
     nd.imask = (uint8_t)imask;
+    nd.trimask = trimask;
+    nd.reserved = 0;
     if (w < o.node_cap) *reinterpret_cast<Node8*>(o.nodes + (size_t)w * 80u) = nd;
 }
 

@@ -46,6 +46,14 @@ RT_HD double dsub(double a, double b) { return a - b; }
 #endif
 
 RT_HD float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+// (x,y,z) -> components (kx,ky,kz) with kx = kz+1, ky = kz+2 (mod 3); written as selects on two
+// predicates so that the compiler emits SEL, not branches
+RT_HD void permute3(int kz, float x, float y, float z, float& vkx, float& vky, float& vkz) {
+    const bool k0 = kz == 0, k1 = kz == 1;
+    vkz = k0 ? x : (k1 ? y : z);
+    vkx = k0 ? y : (k1 ? z : x);
+    vky = k0 ? z : (k1 ? x : y);
+}
 
 #if defined(__CUDA_ARCH__)
 RT_HD float as_float(uint32_t u) { return __uint_as_float(u); }
@@ -74,15 +82,18 @@ static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
 // Compressed 8-wide node after Ylitie, Karras, Laine 2017 (80 B: five 128-bit loads).
 // Child boxes are quantised to 8 bits per plane relative to (p, 2^e):
 //   plane = p + q * 2^(e-127)    (lo planes rounded down, hi planes rounded up)
-// meta[i]: 0 = empty slot; inner child = 0b001_sssss with sssss = 24 + slot;
-//          leaf = unary triangle count (001/011/111) in the top 3 bits, triangle offset
-//          (relative to tri_base) in the low 5 bits.
+// Slot s (0..7) holds either an inner child (bit s of imask), a leaf of 1..3 triangles
+// (unary count 001/011/111 in bits [3s, 3s+3) of trimask) or nothing.  Inner children are
+// contiguous from child_base in slot order, triangles contiguous from tri_base in bit order:
+//   child index    = child_base + popc(imask   & ((1 << s) - 1))
+//   triangle index = tri_base   + popc(trimask & ((1 << b) - 1))
 struct alignas(16) Node8 {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
-    uint32_t child_base;           // index of the first inner child (children are contiguous)
+    uint32_t child_base;           // index of the first inner child
     uint32_t tri_base;             // index of this node's first triangle record
-    uint8_t meta[8];
+    uint32_t trimask;              // 24 bits, 3 per slot
+    uint32_t reserved;
     uint8_t qlox[8], qloy[8], qloz[8];
     uint8_t qhix[8], qhiy[8], qhiz[8];
 };
@@ -101,7 +112,11 @@ struct Ray {
     // slab test set-up
     float idx, idy, idz;           // 1/d with zero components replaced by +-tiny
     uint32_t octinv;               // 7 - octant, octant bit a = (d_a < 0)
+    // kByteMagic (0x47000000 = 32768.0f), passed in at run time on the device: it must live in
+    // a register so that node_test's PRMT can take the byte selector as its one immediate
+    uint32_t magic;
 };
+constexpr uint32_t kByteMagic = 0x47000000u;
 
 RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox; r.oy = oy; r.oz = oz;
@@ -130,6 +145,7 @@ RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, f
     r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
     const uint32_t oct = (sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u);
     r.octinv = 7u - oct;
+    r.magic = kByteMagic;
 }
 
 // ------------------------------------------------------------------ watertight triangle test
@@ -142,18 +158,13 @@ struct TriHit { float t, U, V, W, det; };
 
 RT_HD bool tri_test(const Ray& r, float v0x, float v0y, float v0z, float v1x, float v1y, float v1z,
                     float v2x, float v2y, float v2z, TriHit& h) {
-    const int kz = r.kz;
-    const int kx = kz == 2 ? 0 : kz + 1;
-    const int ky = kx == 2 ? 0 : kx + 1;
-    const float Akx = fsub(sel3(kx, v0x, v0y, v0z), r.okx);
-    const float Aky = fsub(sel3(ky, v0x, v0y, v0z), r.oky);
-    const float Akz = fsub(sel3(kz, v0x, v0y, v0z), r.okz);
-    const float Bkx = fsub(sel3(kx, v1x, v1y, v1z), r.okx);
-    const float Bky = fsub(sel3(ky, v1x, v1y, v1z), r.oky);
-    const float Bkz = fsub(sel3(kz, v1x, v1y, v1z), r.okz);
-    const float Ckx = fsub(sel3(kx, v2x, v2y, v2z), r.okx);
-    const float Cky = fsub(sel3(ky, v2x, v2y, v2z), r.oky);
-    const float Ckz = fsub(sel3(kz, v2x, v2y, v2z), r.okz);
+    float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
+    permute3(r.kz, v0x, v0y, v0z, Akx, Aky, Akz);
+    permute3(r.kz, v1x, v1y, v1z, Bkx, Bky, Bkz);
+    permute3(r.kz, v2x, v2y, v2z, Ckx, Cky, Ckz);
+    Akx = fsub(Akx, r.okx); Aky = fsub(Aky, r.oky); Akz = fsub(Akz, r.okz);
+    Bkx = fsub(Bkx, r.okx); Bky = fsub(Bky, r.oky); Bkz = fsub(Bkz, r.okz);
+    Ckx = fsub(Ckx, r.okx); Cky = fsub(Cky, r.oky); Ckz = fsub(Ckz, r.okz);
     const float Ax = ffma(-r.Sx, Akz, Akx), Ay = ffma(-r.Sy, Akz, Aky);
     const float Bx = ffma(-r.Sx, Bkz, Bkx), By = ffma(-r.Sy, Bkz, Bky);
     const float Cx = ffma(-r.Sx, Ckz, Ckx), Cy = ffma(-r.Sy, Ckz, Cky);
@@ -206,12 +217,38 @@ RT_HD HitAttr tri_attr(const TriHit& h, float v0x, float v0y, float v0z, float v
 }
 
 // ------------------------------------------------------------------ BVH8 node test
-// Returns the 32-bit hit mask of Ylitie et al.: bits 24..31 = inner children ordered by
-// traversal priority (slot ^ octinv), bits 0..23 = triangles of hit leaf slots.
-// The slab test is conservative: with a = 2^e * idir, b = (p - o) * idir,
-//   t_plane = q*a + b  has |error| <= ~5u(256|a| + |b|), u = 2^-24, which is added to the far
-// and subtracted from the near planes.  NaNs drop out of fminf/fmaxf, which only widens.
-RT_HD float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+// Returns the 32-bit hit mask of Ylitie et al.: bits 24..31 = hit inner children ordered by
+// traversal priority (bit 24 + (slot ^ octinv)), bits 0..23 = triangles of hit leaf slots
+// (bit positions of trimask).
+//
+// Slab test, conservative and branch-free.  With a = 2^e * idir, b = (p - o) * idir a plane
+// sits at t = q*a + b.  The byte q is turned into a float without an I2F: PRMT drops it into
+// bits 8..15 of 0x47000000, which reads 32768 + q, and the 32768*a is pre-subtracted from b:
+//   t = fma(32768 + q, a, b - 32768*a)
+// Rounding: |error| <= ~6u(256|a| + |b|) + |a|/512, u = 2^-24; that margin is subtracted from
+// the near and added to the far planes.  NaNs drop out of fminf/fmaxf, which only widens.
+#if defined(__CUDA_ARCH__)
+// byte I of w -> bits 8..15 of `magic` (= 0x47000000 held in a register so that the selector
+// can be the PRMT immediate)
+template <int I>
+RT_HD float byte_plus_32768(uint32_t w, uint32_t magic) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(magic), "n"(0x7604 | (I << 4)));
+    return __uint_as_float(d);
+}
+#else
+template <int I>
+RT_HD float byte_plus_32768(uint32_t w, uint32_t magic) {
+    return as_float(magic | (((w >> (8u * I)) & 0xffu) << 8));
+}
+#endif
+
+RT_HD uint32_t spread3(uint32_t x) {   // bit i (0..7) -> bit 3i
+    x = (x | (x << 8)) & 0x0000f00fu;
+    x = (x | (x << 4)) & 0x000c30c3u;
+    x = (x | (x << 2)) & 0x00249249u;
+    return x;
+}
 
 RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
                          float tmin, float tmax) {
@@ -221,19 +258,21 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
     const float sz = as_float(((n0.w >> 16) & 0xffu) << 23);
     const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
     const float bx = (px - r.ox) * r.idx, by = (py - r.oy) * r.idy, bz = (pz - r.oz) * r.idz;
-    const float ku = 3.0e-7f;   // 5 * 2^-24
-    const float ex = ku * (256.0f * fabsf(ax) + fabsf(bx));
-    const float ey = ku * (256.0f * fabsf(ay) + fabsf(by));
-    const float ez = ku * (256.0f * fabsf(az) + fabsf(bz));
-    const float bnx = bx - ex, bfx = bx + ex;
-    const float bny = by - ey, bfy = by + ey;
-    const float bnz = bz - ez, bfz = bz + ez;
+    const float ku = 3.6e-7f;            // 6 * 2^-24
+    const float kq = 256.0f * ku + 0.00390625f;   // + 1/256 for the pre-subtraction
+    const float ex = fmaf(kq, fabsf(ax), ku * fabsf(bx));
+    const float ey = fmaf(kq, fabsf(ay), ku * fabsf(by));
+    const float ez = fmaf(kq, fabsf(az), ku * fabsf(bz));
+    const float cnx = fmaf(-32768.0f, ax, bx - ex), cfx = fmaf(-32768.0f, ax, bx + ex);
+    const float cny = fmaf(-32768.0f, ay, by - ey), cfy = fmaf(-32768.0f, ay, by + ey);
+    const float cnz = fmaf(-32768.0f, az, bz - ez), cfz = fmaf(-32768.0f, az, bz + ez);
     // near/far plane bytes by ray octant: d >= 0 -> near = lo, far = hi
     const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
     // words: n2 = (qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7])
     //        n3 = (qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7])
     //        n4 = (qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7])
-    uint32_t hitmask = 0;
+    uint32_t hm8 = 0;
+    const uint32_t magic = r.magic;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
@@ -241,24 +280,30 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
         const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
         const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
         const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
-        const uint32_t meta4 = half ? n1.w : n1.z;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float tnx = fmaf(byte_f(nx, i), ax, bnx), tfx = fmaf(byte_f(fx, i), ax, bfx);
-            const float tny = fmaf(byte_f(ny, i), ay, bny), tfy = fmaf(byte_f(fy, i), ay, bfy);
-            const float tnz = fmaf(byte_f(nz, i), az, bnz), tfz = fmaf(byte_f(fz, i), az, bfz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            const uint32_t meta = (meta4 >> (8 * i)) & 0xffu;
-            if (tn <= tf) {
-                const uint32_t bits = meta >> 5;
-                const uint32_t pos = meta & 0x1fu;
-                const uint32_t shift = pos >= 24u ? (pos ^ r.octinv) : pos;
-                hitmask |= bits << shift;
-            }
+#define RT_SLAB(I)                                                                                              \
+        {                                                                                                       \
+            const float tnx = fmaf(byte_plus_32768<I>(nx, magic), ax, cnx), tfx = fmaf(byte_plus_32768<I>(fx, magic), ax, cfx); \
+            const float tny = fmaf(byte_plus_32768<I>(ny, magic), ay, cny), tfy = fmaf(byte_plus_32768<I>(fy, magic), ay, cfy); \
+            const float tnz = fmaf(byte_plus_32768<I>(nz, magic), az, cnz), tfz = fmaf(byte_plus_32768<I>(fz, magic), az, cfz); \
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                          \
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                          \
+            hm8 |= (tn <= tf) ? (1u << (4 * half + I)) : 0u;                                                    \
         }
+        RT_SLAB(0) RT_SLAB(1) RT_SLAB(2) RT_SLAB(3)
+#undef RT_SLAB
     }
-    return hitmask;
+    const uint32_t imask = n0.w >> 24;
+    // inner hits: move slot s to priority position s ^ octinv (three conditional delta swaps)
+    uint32_t in8 = hm8 & imask;
+    {
+        const uint32_t m1 = (r.octinv & 1u) ? 0x55u : 0u, m2 = (r.octinv & 2u) ? 0x33u : 0u, m4 = (r.octinv & 4u) ? 0x0fu : 0u;
+        uint32_t t;
+        t = ((in8 >> 1) ^ in8) & m1; in8 ^= t | (t << 1);
+        t = ((in8 >> 2) ^ in8) & m2; in8 ^= t | (t << 2);
+        t = ((in8 >> 4) ^ in8) & m4; in8 ^= t | (t << 4);
+    }
+    const uint32_t tri24 = (spread3(hm8) * 7u) & n1.z;
+    return (in8 << 24) | tri24;
 }
 
 }  // namespace rt

@@ -6,8 +6,10 @@
 // programs (triro/backend/shaders.cu:67-246), including the strided ray fetch getRay
 // (shaders.cu:27-63).
 //
-// Execution model: persistent CTAs (grid = SMs x resident CTAs); each warp repeatedly claims
-// 32 consecutive rays from a global counter, one ray per lane; traversal is rt::traverse().
+// Execution model: persistent CTAs (grid = SMs x resident CTAs), one ray per lane.  A warp
+// advances all its rays one wide node at a time (rt::trav_step) and, whenever fewer than
+// kRefillThreshold lanes are still busy, retires the finished rays and re-fills those lanes
+// from a global ray counter with one warp-aggregated atomic (Aila & Laine 2009).
 #include <type_traits>
 #include "rt_api.h"
 #include "rt_traverse.cuh"
@@ -23,6 +25,7 @@ struct TraceParams {
     rt_ray_desc rays;
     int o_packed, d_packed;      // 1 = row-major contiguous [n,3] -> offset = 3*r
     float tmax;
+    uint32_t byte_magic;         // rt::kByteMagic, kept opaque to ptxas (see rt_core.cuh)
     unsigned long long* ray_counter;
     // outputs (per mode)
     uint8_t* hit;
@@ -64,11 +67,10 @@ template <class S>
 struct AllHitsVisitor : S {
     float tmax;
     int32_t count = 0;
-    int max_hits;
-    uint4* out;
-    const uint8_t* tris;
-    __device__ __forceinline__ AllHitsVisitor(float tmax0, int mh, uint4* o, const uint8_t* t)
-        : tmax(tmax0), max_hits(mh), out(o), tris(t) {}
+    int max_hits = 0;
+    uint4* out = nullptr;
+    const uint8_t* tris = nullptr;
+    __device__ __forceinline__ explicit AllHitsVisitor(float tmax0) : tmax(tmax0) {}
     __device__ __forceinline__ bool hit(const Ray&, const TriHit& h, int32_t prim, uint32_t slot) {
         if (h.t > 0.0f && h.t < tmax) {
             if (count < max_hits) {
@@ -85,42 +87,92 @@ struct AllHitsVisitor : S {
     }
 };
 
+template <int MODE, class S>
+struct VisitorOf {
+    using type = typename std::conditional<
+        MODE == kClosest || MODE == kFirst, ClosestVisitor<S>,
+        typename std::conditional<MODE == kAny, AnyVisitor<S>,
+                                  typename std::conditional<MODE == kAllHits, AllHitsVisitor<S>, CountVisitor<S>>::type>::type>::type;
+};
+
+// A warp re-fills its finished lanes from the global ray counter as soon as fewer than
+// kRefillThreshold lanes are still traversing.
+constexpr int kRefillThreshold = 24;
+
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ TraceParams p) {
     using S = typename std::conditional<STATS, Stats, NoStats>::type;
+    using Vis = typename VisitorOf<MODE, S>::type;
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
     const uint8_t* tris = p.blob + hdr->tris_offset;
     const uint8_t* nodes = p.blob + hdr->nodes_offset;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t nray = p.rays.nray;
     LocalStack stack;
     unsigned long long st_nodes = 0, st_tris = 0, st_rays = 0, st_hits = 0;
     bool any_inside = false, any_broken = false;
 
+    Vis vis(p.tmax);
+    Trav tv;
+    Ray ray;
+    int64_t r = -1;
+    bool active = false, exhausted = false;
+    int phase = 0;
+    int32_t count_plus = 0;
+    trav_init(tv);
+
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(p.ray_counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if ((int64_t)base >= nray) break;
-        const int64_t r = (int64_t)base + lane;
-        if (r < nray) {
-            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_packed, r);
-            const int64_t os = p.rays.o_stride[3];
-            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
-            float dx, dy, dz;
-            if (MODE == kContains) {
-                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
-            } else {
-                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_packed, r);
-                const int64_t ds = p.rays.d_stride[3];
-                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+        // ---- refill idle lanes with fresh rays (one atomic per warp)
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !exhausted) {
+            const int n_idle = __popc(idle);
+            const int leader = __ffs((int)idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if ((int64_t)base + n_idle >= nray) exhausted = true;
+            if (!active) {
+                r = (int64_t)base + __popc(idle & lt_mask);
+                if (r < nray) {
+                    const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_packed, r);
+                    const int64_t os = p.rays.o_stride[3];
+                    const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
+                    float dx, dy, dz;
+                    if (MODE == kContains) {
+                        dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+                    } else {
+                        const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_packed, r);
+                        const int64_t ds = p.rays.d_stride[3];
+                        dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+                    }
+                    ray_setup(ray, ox, oy, oz, dx, dy, dz);
+                    ray.magic = p.byte_magic;
+                    trav_init(tv);
+                    vis = Vis(p.tmax);
+                    if constexpr (MODE == kAllHits) {
+                        vis.max_hits = p.max_hits; vis.out = p.staging + (size_t)r * p.max_hits; vis.tris = tris;
+                    }
+                    phase = 0;
+                    active = true;
+                }
             }
-            Ray ray;
-            ray_setup(ray, ox, oy, oz, dx, dy, dz);
-            if (MODE == kClosest || MODE == kFirst) {
-                ClosestVisitor<S> vis(p.tmax);
-                traverse(nodes, tris, ray, vis, stack);
-                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.prim >= 0; }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+
+        // ---- traverse until too few lanes are left running
+        bool fin = !active;
+        const int threshold = exhausted ? 1 : kRefillThreshold;
+        for (;;) {
+            if (!fin) fin = trav_step(nodes, tris, ray, vis, stack, tv);
+            if (__popc(__ballot_sync(0xffffffffu, !fin)) < threshold) break;
+        }
+
+        // ---- retire finished rays
+        if (active && fin) {
+            if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; }
+            if constexpr (MODE == kClosest || MODE == kFirst) {
+                if (STATS) st_hits += vis.prim >= 0;
                 if (MODE == kFirst) {
                     if (p.tri) p.tri[r] = vis.prim;
                 } else if (p.hit) {
@@ -143,36 +195,39 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
                         p.uv[2 * r] = 0.f; p.uv[2 * r + 1] = 0.f;
                     }
                 }
-            } else if (MODE == kAny) {
-                AnyVisitor<S> vis(p.tmax);
-                traverse(nodes, tris, ray, vis, stack);
-                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.found; }
+                active = false;
+            } else if constexpr (MODE == kAny) {
+                if (STATS) st_hits += vis.found;
                 if (p.hit) p.hit[r] = vis.found ? 1 : 0;
-            } else if (MODE == kCount) {
-                CountVisitor<S> vis(p.tmax);
-                traverse(nodes, tris, ray, vis, stack);
-                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; st_hits += vis.count > 0; }
+                active = false;
+            } else if constexpr (MODE == kCount) {
+                if (STATS) st_hits += vis.count > 0;
                 if (p.count) p.count[r] = vis.count;
-            } else if (MODE == kAllHits) {
-                AllHitsVisitor<S> vis(p.tmax, p.max_hits, p.staging + (size_t)r * p.max_hits, tris);
-                traverse(nodes, tris, ray, vis, stack);
+                active = false;
+            } else if constexpr (MODE == kAllHits) {
                 p.count[r] = vis.count < p.max_hits ? vis.count : p.max_hits;
-            } else if (MODE == kContains) {
-                // reference: ray_optix.py:238-267
-                const bool inside = ox > p.aabb_lo[0] && oy > p.aabb_lo[1] && oz > p.aabb_lo[2] &&
-                                    ox < p.aabb_hi[0] && oy < p.aabb_hi[1] && oz < p.aabb_hi[2];
-                CountVisitor<S> plus(p.tmax);
-                traverse(nodes, tris, ray, plus, stack);
-                Ray back;
-                ray_setup(back, ox, oy, oz, -dx, -dy, -dz);
-                CountVisitor<S> minus(p.tmax);
-                traverse(nodes, tris, back, minus, stack);
-                const bool agree = (plus.count & 1) && (minus.count & 1);
-                const bool brk = !agree && (plus.count == 0 || minus.count == 0);
-                p.contain[r] = (inside && agree) ? 1 : 0;
-                p.broken[r] = brk ? 1 : 0;
-                any_inside |= inside;
-                any_broken |= brk;
+                active = false;
+            } else if constexpr (MODE == kContains) {
+                // reference: ray_optix.py:238-267 — count along +dir, then along -dir
+                if (phase == 0) {
+                    count_plus = vis.count;
+                    const float ox = ray.ox, oy = ray.oy, oz = ray.oz;
+                    ray_setup(ray, ox, oy, oz, -p.dir[0], -p.dir[1], -p.dir[2]);
+                    ray.magic = p.byte_magic;
+                    trav_init(tv);
+                    vis = Vis(p.tmax);
+                    phase = 1;
+                } else {
+                    const bool inside = ray.ox > p.aabb_lo[0] && ray.oy > p.aabb_lo[1] && ray.oz > p.aabb_lo[2] &&
+                                        ray.ox < p.aabb_hi[0] && ray.oy < p.aabb_hi[1] && ray.oz < p.aabb_hi[2];
+                    const bool agree = (count_plus & 1) && (vis.count & 1);
+                    const bool brk = !agree && (count_plus == 0 || vis.count == 0);
+                    p.contain[r] = (inside && agree) ? 1 : 0;
+                    p.broken[r] = brk ? 1 : 0;
+                    any_inside |= inside;
+                    any_broken |= brk;
+                    active = false;
+                }
             }
         }
     }
@@ -239,6 +294,7 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     p.o_packed = is_packed(rays->shape, rays->o_stride) ? 1 : 0;
     p.d_packed = (MODE != kContains && is_packed(rays->shape, rays->d_stride)) ? 1 : 0;
     p.tmax = RT_TMAX_DEFAULT;
+    p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
     RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
     static thread_local int per_sm_cache[2][8] = {{0}};

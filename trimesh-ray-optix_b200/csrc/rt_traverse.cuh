@@ -24,54 +24,69 @@ RT_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 RT_HD U4 ldg128(const void* p) { return *reinterpret_cast<const U4*>(p); }
 #endif
 
-struct Stack2 { uint32_t x, y; };
+// Per-ray traversal state: the current node group (gx = child_base, gy = inner hit bits 24..31 |
+// imask) and the stack depth.  trav_step() advances one wide node: pick the nearest pending
+// child, test its 8 slots, intersect the triangles of the hit leaf slots, pop when the group is
+// exhausted.  Splitting traversal into steps lets the kernel re-fill finished lanes of a warp
+// between steps (persistent threads with dynamic ray fetch, Aila & Laine 2009).
+struct Trav {
+    uint32_t gx, gy;
+    int sp;
+};
+RT_HD void trav_init(Trav& t) { t.gx = 0u; t.gy = 0x80000000u; t.sp = 0; }   // root group: node 0, top priority
 
 // Visitor concept:
 //   float tmax            current far limit of the ray interval (closest-hit shrinks it)
 //   bool hit(const Ray&, const TriHit&, int32_t prim, uint32_t tri_slot)  -> true = terminate ray
 //   void count_node(), count_tri()   instrumentation hooks
+// Returns true when the ray is finished.
+template <class Visitor, class StackT>
+RT_HD bool trav_step(const uint8_t* __restrict__ nodes, const uint8_t* __restrict__ tris, const Ray& r,
+                     Visitor& vis, StackT& stack, Trav& t) {
+    if (t.gy & 0xff000000u) {
+        const uint32_t hits = t.gy;
+        const int bit = 31 - clz32(hits);
+        t.gy &= ~(1u << bit);
+        if (t.gy & 0xff000000u) { stack.push(t.sp, t.gx, t.gy); ++t.sp; }
+        const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+        const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot));
+        const uint8_t* np = nodes + (size_t)(t.gx + rel) * 80u;
+        const U4 n0 = ldg128(np), n1 = ldg128(np + 16), n2 = ldg128(np + 32), n3 = ldg128(np + 48),
+                 n4 = ldg128(np + 64);
+        vis.count_node();
+        const uint32_t hm = node_test(r, n0, n1, n2, n3, n4, 0.0f, vis.tmax);
+        t.gx = n1.x;
+        t.gy = (hm & 0xff000000u) | (n0.w >> 24);
+        uint32_t ty = hm & 0x00ffffffu;
+        const uint32_t tx = n1.y, tmask = n1.z;
+        while (ty) {
+            const int b = ffs32(ty) - 1;
+            ty &= ty - 1u;
+            const uint32_t slot_t = tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b));
+            const uint8_t* tp = tris + (size_t)slot_t * 48u;
+            const U4 a = ldg128(tp), bb = ldg128(tp + 16), c = ldg128(tp + 32);
+            vis.count_tri();
+            TriHit h;
+            if (tri_test(r, as_float(a.x), as_float(a.y), as_float(a.z), as_float(bb.x), as_float(bb.y),
+                         as_float(bb.z), as_float(c.x), as_float(c.y), as_float(c.z), h)) {
+                if (vis.hit(r, h, (int32_t)a.w, slot_t)) return true;
+            }
+        }
+    }
+    if (!(t.gy & 0xff000000u)) {
+        if (t.sp == 0) return true;
+        --t.sp;
+        stack.pop(t.sp, t.gx, t.gy);
+    }
+    return false;
+}
+
 template <class Visitor, class StackT>
 RT_HD void traverse(const uint8_t* __restrict__ nodes, const uint8_t* __restrict__ tris, const Ray& r,
                     Visitor& vis, StackT& stack) {
-    uint32_t gx = 0u, gy = 0x80000000u;   // root group: node 0 with top priority
-    int sp = 0;
-    for (;;) {
-        if (gy & 0xff000000u) {
-            const uint32_t hits = gy;
-            const int bit = 31 - clz32(hits);
-            gy &= ~(1u << bit);
-            if (gy & 0xff000000u) { stack.push(sp, gx, gy); ++sp; }
-            const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
-            const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot));
-            const uint8_t* np = nodes + (size_t)(gx + rel) * 80u;
-            const U4 n0 = ldg128(np), n1 = ldg128(np + 16), n2 = ldg128(np + 32), n3 = ldg128(np + 48),
-                     n4 = ldg128(np + 64);
-            vis.count_node();
-            const uint32_t hm = node_test(r, n0, n1, n2, n3, n4, 0.0f, vis.tmax);
-            gx = n1.x;
-            gy = (hm & 0xff000000u) | (n0.w >> 24);
-            uint32_t ty = hm & 0x00ffffffu;
-            const uint32_t tx = n1.y;
-            while (ty) {
-                const int b = ffs32(ty) - 1;
-                ty &= ty - 1u;
-                const uint32_t slot_t = tx + (uint32_t)b;
-                const uint8_t* tp = tris + (size_t)slot_t * 48u;
-                const U4 a = ldg128(tp), bb = ldg128(tp + 16), c = ldg128(tp + 32);
-                vis.count_tri();
-                TriHit h;
-                if (tri_test(r, as_float(a.x), as_float(a.y), as_float(a.z), as_float(bb.x), as_float(bb.y),
-                             as_float(bb.z), as_float(c.x), as_float(c.y), as_float(c.z), h)) {
-                    if (vis.hit(r, h, (int32_t)a.w, slot_t)) return;
-                }
-            }
-        }
-        if (!(gy & 0xff000000u)) {
-            if (sp == 0) return;
-            --sp;
-            stack.pop(sp, gx, gy);
-        }
-    }
+    Trav t;
+    trav_init(t);
+    while (!trav_step(nodes, tris, r, vis, stack, t)) {}
 }
 
 // ------------------------------------------------------------------ visitors
