@@ -10,6 +10,7 @@
 // advances all its rays one wide node at a time (rt::trav_step) and, whenever fewer than
 // kRefillThreshold lanes are still busy, retires the finished rays and re-fills those lanes
 // from a global ray counter with one warp-aggregated atomic (Aila & Laine 2009).
+#include <stdlib.h>
 #include <type_traits>
 #include "rt_api.h"
 #include "rt_traverse.cuh"
@@ -23,7 +24,8 @@ constexpr int kTraceThreads = 128;
 struct TraceParams {
     const uint8_t* blob;
     rt_ray_desc rays;
-    int o_packed, d_packed;      // 1 = row-major contiguous [n,3] -> offset = 3*r
+    int o_mode, d_mode;          // kGeneral / kPacked (offset 3*r) / kConstant (offset 0) / kGeneral32
+    int refill_threshold;
     float tmax;
     uint32_t byte_magic;         // rt::kByteMagic, kept opaque to ptxas (see rt_core.cuh)
     unsigned long long* ray_counter;
@@ -52,8 +54,17 @@ struct LocalStack {
     __device__ __forceinline__ void pop(int sp, uint32_t& x, uint32_t& y) { const uint2 v = e[sp]; x = v.x; y = v.y; }
 };
 
-__device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int64_t stride[4], int packed, int64_t r) {
-    if (packed) return 3 * r;
+enum FetchMode { kGeneral = 0, kPacked = 1, kConstant = 2, kGeneral32 = 3 };
+
+__device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int64_t stride[4], int mode, int64_t r) {
+    if (mode == kPacked) return 3 * r;
+    if (mode == kConstant) return 0;
+    if (mode == kGeneral32) {   // fewer than 2^31 rays: 32-bit divisions
+        const uint32_t s2 = (uint32_t)shape[2], s1 = (uint32_t)shape[1], rr = (uint32_t)r;
+        const uint32_t q = rr / s2, i2 = rr - q * s2;
+        const uint32_t i0 = q / s1, i1 = q - i0 * s1;
+        return (int64_t)i0 * stride[0] + (int64_t)i1 * stride[1] + (int64_t)i2 * stride[2];
+    }
     const int64_t i2 = r % shape[2];
     const int64_t q = r / shape[2];
     const int64_t i1 = q % shape[1];
@@ -135,14 +146,14 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
             if (!active) {
                 r = (int64_t)base + __popc(idle & lt_mask);
                 if (r < nray) {
-                    const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_packed, r);
+                    const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
                     const int64_t os = p.rays.o_stride[3];
                     const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
                     float dx, dy, dz;
                     if (MODE == kContains) {
                         dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
                     } else {
-                        const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_packed, r);
+                        const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
                         const int64_t ds = p.rays.d_stride[3];
                         dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
                     }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
 
         // ---- traverse until too few lanes are left running
         bool fin = !active;
-        const int threshold = exhausted ? 1 : kRefillThreshold;
+        const int threshold = exhausted ? 1 : p.refill_threshold;
         for (;;) {
             if (!fin) fin = trav_step(nodes, tris, ray, vis, stack, tv);
             if (__popc(__ballot_sync(0xffffffffu, !fin)) < threshold) break;
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
     }
 }
 
+static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t nray);
 static bool is_packed(const int64_t shape[4], const int64_t stride[4]) {
     // row-major contiguous [s0,s1,s2,3]; dimensions of extent 1 may carry any stride
     if (stride[3] != 1) return false;
@@ -261,6 +273,26 @@ static bool is_packed(const int64_t shape[4], const int64_t stride[4]) {
         expect *= shape[i];
     }
     return true;
+}
+
+static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t nray) {
+    if (is_packed(shape, stride)) return kPacked;
+    bool constant = true;
+    for (int i = 0; i < 3; ++i) if (shape[i] != 1 && stride[i] != 0) constant = false;
+    if (constant) return kConstant;                    // stride-0 broadcast of one vector
+    return nray < ((int64_t)1 << 31) ? kGeneral32 : kGeneral;
+}
+
+static int refill_threshold_from_env() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("TRIRO_REFILL_THRESHOLD");
+        int v = e ? atoi(e) : kRefillThreshold;
+        if (v < 1) v = 1;
+        if (v > 32) v = 32;
+        cached = v;
+    }
+    return cached;
 }
 
 static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
@@ -291,8 +323,9 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "%s: no CUDA device", fn);
     p.blob = reinterpret_cast<const uint8_t*>(blob);
     p.rays = *rays;
-    p.o_packed = is_packed(rays->shape, rays->o_stride) ? 1 : 0;
-    p.d_packed = (MODE != kContains && is_packed(rays->shape, rays->d_stride)) ? 1 : 0;
+    p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
+    p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
+    p.refill_threshold = refill_threshold_from_env();
     p.tmax = RT_TMAX_DEFAULT;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
