@@ -1,0 +1,69 @@
+"""Host-side logic of the Python mirror that does not need a GPU: ray descriptor marshalling
+(reference fillArray, ray.cpp:151-159), input validation (ray.cpp:104-123), shard arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from triro import distributed as tdist
+from triro.backend import ops
+
+
+def test_ray_desc_right_aligns_shape_and_strides_like_fill_array():
+    o = torch.zeros(5, 7, 3)
+    d = torch.zeros(7, 5, 3).transpose(0, 1)
+    rd, batch = ops.make_ray_desc(o, d)
+    assert batch == (5, 7) and rd.nray == 35
+    assert list(rd.shape) == [1, 5, 7, 3]
+    assert list(rd.o_stride) == [0, 21, 3, 1]
+    assert list(rd.d_stride) == [0, 3, 15, 1]
+    b = torch.tensor([0.0, 0.0, 3.0]).broadcast_to(4, 6, 2, 3)
+    rd, batch = ops.make_ray_desc(b, b)
+    assert list(rd.shape) == [4, 6, 2, 3] and list(rd.o_stride) == [0, 0, 0, 1] and rd.nray == 48
+    rd, batch = ops.make_ray_desc(torch.zeros(3), torch.zeros(3))
+    assert batch == () and rd.nray == 1 and list(rd.shape) == [1, 1, 1, 3]
+    rd, _ = ops.make_ray_desc(torch.zeros(0, 3), torch.zeros(0, 3))
+    assert rd.nray == 0
+
+
+def test_ray_desc_rejects_what_the_reference_silently_mishandles():
+    with pytest.raises(ValueError):
+        ops.make_ray_desc(torch.zeros(2, 2, 2, 2, 3), torch.zeros(2, 2, 2, 2, 3))      # > 3 batch dims
+    with pytest.raises(ValueError):
+        ops.make_ray_desc(torch.zeros(4, 2), torch.zeros(4, 2))                        # last dim != 3
+    with pytest.raises(ValueError):
+        ops.make_ray_desc(torch.zeros(4, 3), torch.zeros(5, 3))                        # shape mismatch
+
+
+def test_tensor_input_check_mirrors_reference_conditions():
+    with pytest.raises(ValueError, match="cuda"):
+        ops.tensor_input_check(torch.zeros(2, 3))                                      # not on the GPU
+    with pytest.raises(ValueError):
+        ops.tensor_input_check("not a tensor")
+
+
+def test_constructor_contract():
+    from triro.ray.ray_optix import RayMeshIntersector
+
+    with pytest.raises(ValueError, match="Either 'mesh' or 'vertices' and 'faces'"):
+        RayMeshIntersector()
+    with pytest.raises(ValueError):
+        RayMeshIntersector(vertices=torch.zeros(3, 3))
+
+
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 4), (10, 3), (8_294_400, 8), (1_000_000_000, 8), (7, 8)])
+def test_shard_bounds_partition_the_ray_index_space(n, world):
+    prev = 0
+    for r in range(world):
+        lo, hi = tdist.shard_bounds(n, world, r)
+        assert lo == prev and lo <= hi <= n
+        prev = hi
+    assert prev == n
+    per = -(-n // world) if world else n
+    assert all(tdist.shard_bounds(n, world, r)[1] - tdist.shard_bounds(n, world, r)[0] <= per for r in range(world))
+
+
+def test_slice_rays_handles_strided_and_broadcast_batches():
+    d = torch.arange(2 * 3 * 4 * 3, dtype=torch.float32).reshape(2, 3, 4, 3).transpose(0, 2)
+    o = torch.tensor([1.0, 2.0, 3.0]).broadcast_to(d.shape)
+    so, sd = tdist.slice_rays(o, d, 5, 17)
+    assert so.shape == (12, 3) and torch.equal(sd, d.reshape(-1, 3)[5:17]) and torch.all(so == torch.tensor([1.0, 2.0, 3.0]))

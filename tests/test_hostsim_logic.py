@@ -1,0 +1,104 @@
+"""CPU-only coverage of the product's builder / traversal LOGIC: the __host__ __device__ functions of
+trimesh-ray-optix_b200/csrc (Morton codes, Karras hierarchy, BVH8 collapse + quantisation, node
+test, watertight triangle test, traversal state machine) are stepped on the CPU by tests/hostsim
+and compared with the oracle.  (The CUDA kernels themselves are covered by the -m gpu tests.)"""
+import numpy as np
+import pytest
+
+import hostsim
+from oracle import oracle
+from triro import synth
+
+
+def mesh(name):
+    if name.startswith("tri"):
+        n = int(name[3:])
+        rng = np.random.default_rng(n)
+        return rng.uniform(-1, 1, size=(3 * n, 3)).astype(np.float32), np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    if name.startswith("ico"):
+        return synth.icosphere(int(name[3:]))
+    if name == "soup":
+        return synth.triangle_soup(5000, sigma=0.03, seed=3)
+    if name == "hf":
+        return synth.heightfield(48, 24)
+    if name == "cube":
+        return synth.cube()
+    if name == "dup":       # many identical Morton codes: 64 copies of the same triangle + a degenerate one
+        v = np.tile(np.array([[0.5, -0.5, 0], [0, 0.5, 0], [-0.5, -0.5, 0]], np.float32), (65, 1))
+        v[-3:] = 1.0
+        return v, np.arange(195, dtype=np.int32).reshape(65, 3)
+    raise KeyError(name)
+
+
+MESHES = ["tri1", "tri2", "tri3", "tri4", "tri9", "ico0", "ico2", "ico4", "soup", "hf", "cube", "dup"]
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_blob_structure_and_conservative_quantisation(name):
+    v, f = mesh(name)
+    blob = hostsim.build_blob(v, f)
+    code, info = hostsim.check_blob(blob)
+    assert code == 0, f"hs_check_blob -> {code}"
+    assert info["tris"] == len(f)
+    assert np.array_equal(np.sort(hostsim.blob_prims(blob, len(f))), np.arange(len(f)))
+    assert info["depth"] <= 60
+    if len(f) > 64:
+        assert info["nodes"] <= len(f) // 3 + 2        # node pool bound used by rt_bvh_sizes
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_traversal_matches_oracle_mirror_bit_for_bit(name):
+    v, f = mesh(name)
+    blob = hostsim.build_blob(v, f)
+    o, d = synth.random_rays(4000, seed=len(f), box=True)
+    o, d = (o * 1.5).numpy(), d.numpy()
+    # axis-aligned and zero-component directions exercise the slab test's +-tiny substitution
+    d[:200] = np.eye(3, dtype=np.float32)[np.arange(200) % 3] * np.where(np.arange(200) % 2, 1, -1)[:, None]
+    om = oracle.OracleMesh(v, f, use_bvh=False)
+    ref = oracle.query(om, o, d, oracle.MIRROR)
+    got = hostsim.trace(blob, "closest", o, d)
+    for k in ("hit", "front", "tri"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["loc"].view(np.uint32), ref["loc"].view(np.uint32))
+    assert np.array_equal(got["uv"].view(np.uint32), ref["uv"].view(np.uint32))
+    assert np.array_equal(hostsim.trace(blob, "count", o, d)["count"], ref["count"])
+    assert np.array_equal(hostsim.trace(blob, "any", o, d)["hit"], (ref["count"] > 0).astype(np.uint8))
+    assert got["max_stack"] <= hostsim.check_blob(blob)[1]["depth"]
+
+
+def test_traversal_matches_truth_outside_grazing_set():
+    v, f = synth.icosphere(4)
+    blob = hostsim.build_blob(v, f)
+    o, d = synth.pinhole_rays(160, 90)
+    o, d = o.numpy().reshape(-1, 3), d.numpy().reshape(-1, 3)
+    ref = oracle.query(oracle.OracleMesh(v, f), o, d, oracle.TRUTH)
+    got = hostsim.trace(blob, "closest", o, d)
+    clean = ref["flags"] == 0
+    assert clean.mean() > 0.98
+    for k in ("hit", "front", "tri"):
+        assert np.array_equal(got[k][clean], ref[k][clean]), k
+    both = clean & (ref["hit"] == 1)
+    assert np.abs(got["loc"][both] - ref["loc"][both]).max() < 1e-5
+
+
+def test_closest_hit_tie_break_is_by_primitive_index():
+    """Two coincident triangles: the smaller face index wins regardless of BVH order."""
+    tri = np.array([[0.5, -0.5, 0], [0, 0.5, 0], [-0.5, -0.5, 0]], np.float32)
+    v = np.concatenate([tri, tri + [3, 0, 0], tri, tri + [0, 3, 0], tri + [0, 0, -1]]).astype(np.float32)
+    f = np.arange(15, dtype=np.int32).reshape(5, 3)
+    blob = hostsim.build_blob(v, f)
+    o = np.array([[0, 0, 4]], np.float32); d = np.array([[0, 0, -1]], np.float32)
+    assert hostsim.trace(blob, "closest", o, d)["tri"].tolist() == [0]
+    assert hostsim.trace(blob, "count", o, d)["count"].tolist() == [3]
+    assert hostsim.trace(blob, "closest", o, -d)["hit"].tolist() == [0]
+
+
+def test_empty_mesh_and_nan_rays():
+    blob = hostsim.build_blob(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    assert hostsim.check_blob(blob)[0] == 0
+    o = np.array([[0, 0, 3], [np.nan, 0, 3]], np.float32); d = np.array([[0, 0, -1], [0, 0, -1]], np.float32)
+    assert hostsim.trace(blob, "any", o, d)["hit"].tolist() == [0, 0]
+    v, f = synth.icosphere(1)
+    blob = hostsim.build_blob(v, f)
+    d2 = np.array([[0, 0, 0], [0, 0, -1]], np.float32)
+    assert hostsim.trace(blob, "count", o, d2)["count"].tolist() == [0, 0]
