@@ -207,6 +207,19 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             ref[k] = r; inner[k] = bt_expandable(t, r); area[k] = bt_area(t, r);
             ++k;
         }
+        // free slots left: split multi-triangle leaves (largest box first) so that each triangle
+        // gets a tighter slot box — the node test costs the same for 2 or 8 occupied slots
+        while (k < 8) {
+            int best = -1; float ba = -1.0f;
+            for (int i = 0; i < k; ++i)
+                if (!inner[i] && ref[i] < (uint32_t)(t.n - 1) && area[i] > ba) { best = i; ba = area[i]; }
+            if (best < 0) break;
+            const uint32_t b = ref[best];
+            const uint32_t l = t.left[b], r = t.right[b];
+            ref[best] = l; inner[best] = false; area[best] = bt_area(t, l);
+            ref[k] = r; inner[k] = false; area[k] = bt_area(t, r);
+            ++k;
+        }
     }
     // child boxes, kinds
     BBox cb[8];

@@ -243,6 +243,16 @@ RT_HD float byte_plus_32768(uint32_t w, uint32_t magic) {
 }
 #endif
 
+// (acc << 1) | signbit(x)
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t shift_in_sign(float x, uint32_t acc) { return __funnelshift_l(__float_as_uint(x), acc, 1); }
+#else
+RT_HD uint32_t shift_in_sign(float x, uint32_t acc) {
+    union { float f; uint32_t u; } c; c.f = x;
+    return (acc << 1) | (c.u >> 31);
+}
+#endif
+
 RT_HD uint32_t spread3(uint32_t x) {   // bit i (0..7) -> bit 3i
     x = (x | (x << 8)) & 0x0000f00fu;
     x = (x | (x << 4)) & 0x000c30c3u;
@@ -271,10 +281,12 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
     // words: n2 = (qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7])
     //        n3 = (qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7])
     //        n4 = (qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7])
-    uint32_t hm8 = 0;
+    // miss bits are collected from the sign of (tf - tn) with a funnel shift: FADD runs on the FMA
+    // pipe, leaving one ALU-pipe instruction per child (the ALU pipe is the kernel's bottleneck)
+    uint32_t miss = 0;
     const uint32_t magic = r.magic;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 1; half >= 0; --half) {
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
         const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
         const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
@@ -287,11 +299,12 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
             const float tnz = fmaf(byte_plus_32768<I>(nz, magic), az, cnz), tfz = fmaf(byte_plus_32768<I>(fz, magic), az, cfz); \
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                          \
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                          \
-            hm8 |= (tn <= tf) ? (1u << (4 * half + I)) : 0u;                                                    \
+            miss = shift_in_sign(tf - tn, miss);                                                                \
         }
-        RT_SLAB(0) RT_SLAB(1) RT_SLAB(2) RT_SLAB(3)
+        RT_SLAB(3) RT_SLAB(2) RT_SLAB(1) RT_SLAB(0)
 #undef RT_SLAB
     }
+    const uint32_t hm8 = ~miss & 0xffu;
     const uint32_t imask = n0.w >> 24;
     // inner hits: move slot s to priority position s ^ octinv (three conditional delta swaps)
     uint32_t in8 = hm8 & imask;
