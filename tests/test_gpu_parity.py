@@ -449,10 +449,26 @@ def test_trace_stats_counts_agree_with_host_simulation(cuda_device):
     v, f = synth.icosphere(4)
     r = make(v, f)
     o, d = synth.readme_rays(200, device=cuda_device)
-    st = hops.trace_stats(r.as_wrapper, o.contiguous(), d, "closest")
+    # shared-origin rays take the direct (triangles-in-step) schedule, which visits nodes in exactly
+    # the order of the host simulation; the queued schedule may visit a few more (later tmax shrink)
+    st = hops.trace_stats(r.as_wrapper, o, d, "closest")
     sim = hostsim.trace(r.as_wrapper.blob.cpu().numpy(), "closest", flat(o), flat(d))
     assert st["rays"] == 40_000 and st["nodes"] == sim["stats"]["nodes"] and st["tris"] == sim["stats"]["tris"]
     assert st["hits"] == sim["stats"]["hits"]
+    sq = hops.trace_stats(r.as_wrapper, o.contiguous(), d, "closest")          # per-ray origins -> queued schedule
+    assert sq["rays"] == 40_000 and sq["hits"] == st["hits"] and sq["nodes"] >= st["nodes"]
+
+
+def test_direct_and_queued_schedules_give_identical_results(cuda_device):
+    v, f = synth.icosphere(5)
+    r = make(v, f)
+    o, d = synth.pinhole_rays(640, 360, device=cuda_device)
+    a = closest_to_numpy(r.intersects_closest(o, d))                            # broadcast origin: direct
+    b = closest_to_numpy(r.intersects_closest(o.contiguous(), d))               # materialised origins: queued
+    for k in a:
+        assert_bits_equal(a[k], b[k], f"direct vs queued {k}")
+    assert torch.equal(r.intersects_count(o, d), r.intersects_count(o.contiguous(), d))
+    assert torch.equal(r.intersects_any(o, d), r.intersects_any(o.contiguous(), d))
 
 
 # ---------------------------------------------------------------- golden fixture (reference's own host logic)

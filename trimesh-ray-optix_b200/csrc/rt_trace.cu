@@ -25,7 +25,7 @@ struct TraceParams {
     const uint8_t* blob;
     rt_ray_desc rays;
     int o_mode, d_mode;          // kGeneral / kPacked (offset 3*r) / kConstant (offset 0) / kGeneral32
-    int refill_threshold;
+    int refill_threshold, tri_threshold;
     float tmax;
     uint32_t byte_magic;         // rt::kByteMagic, kept opaque to ptxas (see rt_core.cuh)
     unsigned long long* ray_counter;
@@ -107,13 +107,34 @@ struct VisitorOf {
 };
 
 // A warp re-fills its finished lanes from the global ray counter as soon as fewer than
-// kRefillThreshold lanes are still traversing.
-constexpr int kRefillThreshold = 24;
+// `refill_threshold` lanes are still busy (defaults below; TRIRO_REFILL_THRESHOLD overrides).
+constexpr int kRefillThresholdQueued = 20;
+constexpr int kRefillThresholdDirect = 8;
+// Postponed triangle tests: every lane owns a queue of pending triangle record indices in shared
+// memory (s_queue[entry][thread], conflict-free).  Node steps only enqueue; a warp runs a triangle
+// pass (one queued triangle per lane) when at least `tri_threshold` lanes have one pending, when a
+// queue could overflow on the next node (a node yields at most 24 triangles), or when no lane has
+// node work left.  This keeps the ~120-instruction watertight test at high SIMD efficiency instead
+// of running it with the few lanes that happen to hit a leaf in the same step.
+constexpr int kQueueCap = 32;
+constexpr int kQueueHigh = kQueueCap - kNodeMaxTris;   // 8: above this a lane may not take a node step
+constexpr int kTriThreshold = 8;
 
-template <int MODE, bool STATS>
+struct LaneQueue {
+    uint32_t (*q)[kTraceThreads];
+    int len;
+    __device__ __forceinline__ void push(uint32_t v) { q[len][threadIdx.x] = v; ++len; }
+    __device__ __forceinline__ uint32_t pop() { --len; return q[len][threadIdx.x]; }
+};
+
+// QUEUED = postpone triangle tests through the per-lane queue (incoherent batches); otherwise the
+// triangles of a hit leaf slot are tested inside the node step (coherent batches: neighbouring
+// lanes reach their leaves in the same step anyway, and the nearest hit shrinks tmax earlier).
+template <int MODE, bool STATS, bool QUEUED>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ TraceParams p) {
     using S = typename std::conditional<STATS, Stats, NoStats>::type;
     using Vis = typename VisitorOf<MODE, S>::type;
+    __shared__ uint32_t s_queue[QUEUED ? kQueueCap : 1][kTraceThreads];
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
     const uint8_t* tris = p.blob + hdr->tris_offset;
     const uint8_t* nodes = p.blob + hdr->nodes_offset;
@@ -121,6 +142,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t nray = p.rays.nray;
     LocalStack stack;
+    LaneQueue queue;
+    queue.q = s_queue;
+    queue.len = 0;
     unsigned long long st_nodes = 0, st_tris = 0, st_rays = 0, st_hits = 0;
     bool any_inside = false, any_broken = false;
 
@@ -129,115 +153,134 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__
     Ray ray;
     int64_t r = -1;
     bool active = false, exhausted = false;
+    bool nodes_done = true;          // this lane's ray has no node work left
     int phase = 0;
     int32_t count_plus = 0;
     trav_init(tv);
 
     for (;;) {
-        // ---- refill idle lanes with fresh rays (one atomic per warp)
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u && !exhausted) {
-            const int n_idle = __popc(idle);
-            const int leader = __ffs((int)idle) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if ((int64_t)base + n_idle >= nray) exhausted = true;
-            if (!active) {
-                r = (int64_t)base + __popc(idle & lt_mask);
-                if (r < nray) {
-                    const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
-                    const int64_t os = p.rays.o_stride[3];
-                    const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
-                    float dx, dy, dz;
-                    if (MODE == kContains) {
-                        dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+        // ---- 1. retire finished rays, re-fill free lanes (one atomic per warp)
+        const bool finished = active && nodes_done && queue.len == 0;
+        const unsigned free_lanes = __ballot_sync(0xffffffffu, !active || finished);
+        const int busy = 32 - __popc(free_lanes);
+        if (free_lanes != 0u && busy < (exhausted ? 1 : p.refill_threshold)) {
+            if (finished) {
+                if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; }
+                if constexpr (MODE == kClosest || MODE == kFirst) {
+                    if (STATS) st_hits += vis.prim >= 0;
+                    if (MODE == kFirst) {
+                        if (p.tri) p.tri[r] = vis.prim;
+                    } else if (p.hit) {
+                        if (vis.prim >= 0) {
+                            const uint8_t* tp = tris + (size_t)vis.slot * 48u;
+                            const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
+                            const float v0x = as_float(a.x), v0y = as_float(a.y), v0z = as_float(a.z);
+                            const float v1x = as_float(b.x), v1y = as_float(b.y), v1z = as_float(b.z);
+                            const float v2x = as_float(c.x), v2y = as_float(c.y), v2z = as_float(c.z);
+                            TriHit h;
+                            tri_test(ray, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h);
+                            const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+                            p.hit[r] = 1; p.front[r] = tri_front(ray, h) ? 1 : 0; p.tri[r] = vis.prim;
+                            p.loc[3 * r] = at.lx; p.loc[3 * r + 1] = at.ly; p.loc[3 * r + 2] = at.lz;
+                            p.uv[2 * r] = at.uv0; p.uv[2 * r + 1] = at.uv1;
+                        } else {
+                            // reference miss program: shaders.cu:128-135
+                            p.hit[r] = 0; p.front[r] = 0; p.tri[r] = -1;
+                            p.loc[3 * r] = 0.f; p.loc[3 * r + 1] = 0.f; p.loc[3 * r + 2] = 0.f;
+                            p.uv[2 * r] = 0.f; p.uv[2 * r + 1] = 0.f;
+                        }
+                    }
+                    active = false;
+                } else if constexpr (MODE == kAny) {
+                    if (STATS) st_hits += vis.found;
+                    if (p.hit) p.hit[r] = vis.found ? 1 : 0;
+                    active = false;
+                } else if constexpr (MODE == kCount) {
+                    if (STATS) st_hits += vis.count > 0;
+                    if (p.count) p.count[r] = vis.count;
+                    active = false;
+                } else if constexpr (MODE == kAllHits) {
+                    p.count[r] = vis.count < p.max_hits ? vis.count : p.max_hits;
+                    active = false;
+                } else if constexpr (MODE == kContains) {
+                    // reference: ray_optix.py:238-267 — count along +dir, then along -dir
+                    if (phase == 0) {
+                        count_plus = vis.count;
+                        const float ox = ray.ox, oy = ray.oy, oz = ray.oz;
+                        ray_setup(ray, ox, oy, oz, -p.dir[0], -p.dir[1], -p.dir[2]);
+                        ray.magic = p.byte_magic;
+                        trav_init(tv);
+                        vis = Vis(p.tmax);
+                        nodes_done = false;
+                        phase = 1;
                     } else {
-                        const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
-                        const int64_t ds = p.rays.d_stride[3];
-                        dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+                        const bool inside = ray.ox > p.aabb_lo[0] && ray.oy > p.aabb_lo[1] && ray.oz > p.aabb_lo[2] &&
+                                            ray.ox < p.aabb_hi[0] && ray.oy < p.aabb_hi[1] && ray.oz < p.aabb_hi[2];
+                        const bool agree = (count_plus & 1) && (vis.count & 1);
+                        const bool brk = !agree && (count_plus == 0 || vis.count == 0);
+                        p.contain[r] = (inside && agree) ? 1 : 0;
+                        p.broken[r] = brk ? 1 : 0;
+                        any_inside |= inside;
+                        any_broken |= brk;
+                        active = false;
                     }
-                    ray_setup(ray, ox, oy, oz, dx, dy, dz);
-                    ray.magic = p.byte_magic;
-                    trav_init(tv);
-                    vis = Vis(p.tmax);
-                    if constexpr (MODE == kAllHits) {
-                        vis.max_hits = p.max_hits; vis.out = p.staging + (size_t)r * p.max_hits; vis.tris = tris;
-                    }
-                    phase = 0;
-                    active = true;
                 }
             }
-        }
-        if (!__any_sync(0xffffffffu, active)) break;
-
-        // ---- traverse until too few lanes are left running
-        bool fin = !active;
-        const int threshold = exhausted ? 1 : p.refill_threshold;
-        for (;;) {
-            if (!fin) fin = trav_step(nodes, tris, ray, vis, stack, tv);
-            if (__popc(__ballot_sync(0xffffffffu, !fin)) < threshold) break;
-        }
-
-        // ---- retire finished rays
-        if (active && fin) {
-            if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; }
-            if constexpr (MODE == kClosest || MODE == kFirst) {
-                if (STATS) st_hits += vis.prim >= 0;
-                if (MODE == kFirst) {
-                    if (p.tri) p.tri[r] = vis.prim;
-                } else if (p.hit) {
-                    if (vis.prim >= 0) {
-                        const uint8_t* tp = tris + (size_t)vis.slot * 48u;
-                        const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
-                        const float v0x = as_float(a.x), v0y = as_float(a.y), v0z = as_float(a.z);
-                        const float v1x = as_float(b.x), v1y = as_float(b.y), v1z = as_float(b.z);
-                        const float v2x = as_float(c.x), v2y = as_float(c.y), v2z = as_float(c.z);
-                        TriHit h;
-                        tri_test(ray, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h);
-                        const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
-                        p.hit[r] = 1; p.front[r] = tri_front(ray, h) ? 1 : 0; p.tri[r] = vis.prim;
-                        p.loc[3 * r] = at.lx; p.loc[3 * r + 1] = at.ly; p.loc[3 * r + 2] = at.lz;
-                        p.uv[2 * r] = at.uv0; p.uv[2 * r + 1] = at.uv1;
-                    } else {
-                        // reference miss program: shaders.cu:128-135
-                        p.hit[r] = 0; p.front[r] = 0; p.tri[r] = -1;
-                        p.loc[3 * r] = 0.f; p.loc[3 * r + 1] = 0.f; p.loc[3 * r + 2] = 0.f;
-                        p.uv[2 * r] = 0.f; p.uv[2 * r + 1] = 0.f;
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (idle != 0u && !exhausted) {
+                const int n_idle = __popc(idle);
+                const int leader = __ffs((int)idle) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if ((int64_t)base + n_idle >= nray) exhausted = true;
+                if (!active) {
+                    r = (int64_t)base + __popc(idle & lt_mask);
+                    if (r < nray) {
+                        const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
+                        const int64_t os = p.rays.o_stride[3];
+                        const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
+                        float dx, dy, dz;
+                        if (MODE == kContains) {
+                            dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+                        } else {
+                            const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
+                            const int64_t ds = p.rays.d_stride[3];
+                            dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+                        }
+                        ray_setup(ray, ox, oy, oz, dx, dy, dz);
+                        ray.magic = p.byte_magic;
+                        trav_init(tv);
+                        vis = Vis(p.tmax);
+                        if constexpr (MODE == kAllHits) {
+                            vis.max_hits = p.max_hits; vis.out = p.staging + (size_t)r * p.max_hits; vis.tris = tris;
+                        }
+                        phase = 0;
+                        nodes_done = false;
+                        active = true;
                     }
                 }
-                active = false;
-            } else if constexpr (MODE == kAny) {
-                if (STATS) st_hits += vis.found;
-                if (p.hit) p.hit[r] = vis.found ? 1 : 0;
-                active = false;
-            } else if constexpr (MODE == kCount) {
-                if (STATS) st_hits += vis.count > 0;
-                if (p.count) p.count[r] = vis.count;
-                active = false;
-            } else if constexpr (MODE == kAllHits) {
-                p.count[r] = vis.count < p.max_hits ? vis.count : p.max_hits;
-                active = false;
-            } else if constexpr (MODE == kContains) {
-                // reference: ray_optix.py:238-267 — count along +dir, then along -dir
-                if (phase == 0) {
-                    count_plus = vis.count;
-                    const float ox = ray.ox, oy = ray.oy, oz = ray.oz;
-                    ray_setup(ray, ox, oy, oz, -p.dir[0], -p.dir[1], -p.dir[2]);
-                    ray.magic = p.byte_magic;
-                    trav_init(tv);
-                    vis = Vis(p.tmax);
-                    phase = 1;
-                } else {
-                    const bool inside = ray.ox > p.aabb_lo[0] && ray.oy > p.aabb_lo[1] && ray.oz > p.aabb_lo[2] &&
-                                        ray.ox < p.aabb_hi[0] && ray.oy < p.aabb_hi[1] && ray.oz < p.aabb_hi[2];
-                    const bool agree = (count_plus & 1) && (vis.count & 1);
-                    const bool brk = !agree && (count_plus == 0 || vis.count == 0);
-                    p.contain[r] = (inside && agree) ? 1 : 0;
-                    p.broken[r] = brk ? 1 : 0;
-                    any_inside |= inside;
-                    any_broken |= brk;
-                    active = false;
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
+        }
+
+        if constexpr (!QUEUED) {
+            // ---- 2'. one wide node per lane including its triangles
+            if (active && !nodes_done) nodes_done = trav_step(nodes, tris, ray, vis, stack, tv);
+            continue;
+        }
+        // ---- 2. node phase: one wide node per lane; hit leaf slots only enqueue their triangles
+        const bool can_node = active && !nodes_done && queue.len <= kQueueHigh;
+        if (can_node) nodes_done = node_step(nodes, ray, vis, stack, tv, queue);
+
+        // ---- 3. triangle phase: one queued triangle per lane, when enough lanes have one
+        const unsigned want = __ballot_sync(0xffffffffu, queue.len > 0);
+        if (want != 0u) {
+            const bool more_nodes = active && !nodes_done && queue.len <= kQueueHigh;
+            const bool force = !__any_sync(0xffffffffu, more_nodes);
+            if (force || __popc(want) >= p.tri_threshold) {
+                if (queue.len > 0) {
+                    if (tri_one(tris, ray, vis, queue.pop())) { nodes_done = true; queue.len = 0; }   // any-hit: done
                 }
             }
         }
@@ -283,16 +326,10 @@ static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t n
     return nray < ((int64_t)1 << 31) ? kGeneral32 : kGeneral;
 }
 
-static int refill_threshold_from_env() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("TRIRO_REFILL_THRESHOLD");
-        int v = e ? atoi(e) : kRefillThreshold;
-        if (v < 1) v = 1;
-        if (v > 32) v = 32;
-        cached = v;
-    }
-    return cached;
+static int env_int(const char* name, int fallback, int lo, int hi) {
+    const char* e = getenv(name);
+    int v = e ? atoi(e) : fallback;
+    return v < lo ? lo : (v > hi ? hi : v);
 }
 
 static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
@@ -325,21 +362,32 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     p.rays = *rays;
     p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
     p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
-    p.refill_threshold = refill_threshold_from_env();
     p.tmax = RT_TMAX_DEFAULT;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
     RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
-    static thread_local int per_sm_cache[2][8] = {{0}};
-    int& per_sm = per_sm_cache[STATS ? 1 : 0][MODE];
+    // Scheduling heuristic: rays that share one origin (a stride-0 broadcast, i.e. camera / primary
+    // rays, reference README.md:38 and test/performance_test.py:36-41) are coherent and mostly
+    // short: test triangles inside the node step and re-fill lanes late.  Anything else is treated
+    // as incoherent: postponed triangle tests, early re-fill.  TRIRO_TRI_MODE=0/1 overrides.
+    const int queued_default = (MODE != kContains && p.o_mode == kConstant) ? 0 : 1;
+    const bool queued = env_int("TRIRO_TRI_MODE", queued_default, 0, 1) != 0;
+    p.refill_threshold = env_int("TRIRO_REFILL_THRESHOLD", queued ? kRefillThresholdQueued : kRefillThresholdDirect, 1, 32);
+    p.tri_threshold = env_int("TRIRO_TRI_THRESHOLD", kTriThreshold, 1, 32);
+    static thread_local int per_sm_cache[2][2][8] = {{{0}}};
+    int& per_sm = per_sm_cache[queued ? 1 : 0][STATS ? 1 : 0][MODE];
     if (per_sm == 0) {
-        RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS>, kTraceThreads, 0));
+        if (queued)
+            RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS, true>, kTraceThreads, 0));
+        else
+            RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS, false>, kTraceThreads, 0));
         RT_REQUIRE(per_sm > 0, RT_ERR_CUDA, "%s: kernel does not fit an SM", fn);
     }
     int64_t grid = (int64_t)dev.sm_count * per_sm;
     const int64_t need = (rays->nray + kTraceThreads - 1) / kTraceThreads;
     if (grid > need) grid = need;
-    k_trace<MODE, STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+    if (queued) k_trace<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+    else k_trace<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }
