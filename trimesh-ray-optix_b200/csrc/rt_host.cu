@@ -4,11 +4,21 @@
 // rays live in host memory pays H2D + trace + D2H back to back, the way test/performance_test.py
 // moves its result to the CPU.  This entry point pipelines the three over fixed-size ray chunks on
 // kSlots private streams so the PCIe copies of chunk i+1 / i-1 overlap the traversal of chunk i.
+#include <stdlib.h>
 #include "rt_api.h"
 
 namespace rt {
-constexpr int kSlots = 3;
-constexpr int64_t kHostChunk = 1 << 20;   // rays per chunk
+constexpr int kMaxSlots = 8;
+constexpr int kDefaultSlots = 3;
+constexpr int64_t kDefaultChunk = 1 << 21;   // rays per chunk
+
+static int64_t env_i64(const char* name, int64_t fallback, int64_t lo, int64_t hi) {
+    const char* e = getenv(name);
+    int64_t v = e ? atoll(e) : fallback;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+static int host_slots() { return (int)env_i64("TRIRO_HOST_SLOTS", kDefaultSlots, 1, kMaxSlots); }
+static int64_t host_chunk() { return env_i64("TRIRO_HOST_CHUNK", kDefaultChunk, 1024, (int64_t)1 << 26); }
 
 struct SlotLayout {
     size_t origins, directions, hit, front, tri, loc, uv, scratch, bytes;
@@ -28,14 +38,14 @@ static SlotLayout slot_layout(int64_t chunk) {
     l.bytes = off;
     return l;
 }
-static int64_t chunk_for(int64_t nray) { return nray < kHostChunk ? (nray > 0 ? nray : 1) : kHostChunk; }
+static int64_t chunk_for(int64_t nray) { const int64_t c = host_chunk(); return nray < c ? (nray > 0 ? nray : 1) : c; }
 }  // namespace rt
 
 using namespace rt;
 
 extern "C" int rt_host_closest_sizes(int64_t nray, size_t* dev_work_bytes) {
     RT_REQUIRE(nray >= 0 && dev_work_bytes, RT_ERR_INVALID, "rt_host_closest_sizes: bad arguments");
-    *dev_work_bytes = slot_layout(chunk_for(nray)).bytes * kSlots;
+    *dev_work_bytes = slot_layout(chunk_for(nray)).bytes * host_slots();
     return RT_OK;
 }
 
@@ -49,10 +59,15 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
     RT_REQUIRE(((uintptr_t)dev_work & 255) == 0, RT_ERR_INVALID, "rt_host_trace_closest: dev_work must be 256-byte aligned");
     const int64_t chunk = chunk_for(nray);
     const SlotLayout lay = slot_layout(chunk);
+    const int kSlots = host_slots();
     RT_REQUIRE(dev_work_bytes >= lay.bytes * kSlots, RT_ERR_SIZE, "rt_host_trace_closest: dev_work too small");
 
-    cudaStream_t streams[kSlots];
-    int made = 0;
+    // private streams are created once per host thread and device and reused
+    static thread_local cudaStream_t streams[kMaxSlots];
+    static thread_local int made = 0, made_dev = -1;
+    DeviceInfo dev;
+    RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "rt_host_trace_closest: no CUDA device");
+    if (made_dev != dev.device) { made = 0; made_dev = dev.device; }
     int rc = RT_OK;
     for (; made < kSlots; ++made) {
         if (cudaStreamCreateWithFlags(&streams[made], cudaStreamNonBlocking) != cudaSuccess) {
@@ -61,10 +76,16 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
         }
     }
     uint8_t* base = reinterpret_cast<uint8_t*>(dev_work);
-    for (int64_t c = 0, first = 0; rc == RT_OK && first < nray; ++c, first += chunk) {
+    // chunk sizes ramp up (64 Ki, 128 Ki, ... up to `chunk`) so that the first results start
+    // crossing PCIe almost immediately; the D2H direction is the bottleneck of the whole call
+    const int64_t ramp0 = env_i64("TRIRO_HOST_RAMP", 1 << 16, 1024, chunk);
+    int64_t m = 0;
+    for (int64_t c = 0, first = 0; rc == RT_OK && first < nray; ++c, first += m) {
         const int s = (int)(c % kSlots);
         uint8_t* w = base + (size_t)s * lay.bytes;
-        const int64_t m = nray - first < chunk ? nray - first : chunk;
+        int64_t want = c < 20 ? (ramp0 << c) : chunk;
+        if (want > chunk || want <= 0) want = chunk;
+        m = nray - first < want ? nray - first : want;
         cudaStream_t st = streams[s];
         float* d_o = reinterpret_cast<float*>(w + lay.origins);
         float* d_d = reinterpret_cast<float*>(w + lay.directions);
@@ -90,10 +111,9 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_uv + 2 * first, w + lay.uv, (size_t)m * 8, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) { rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: D2H copy failed: %s", cudaGetErrorString(e)); break; }
     }
-    for (int i = 0; i < made; ++i) {
+    for (int i = 0; i < made && i < kSlots; ++i) {
         const cudaError_t e = cudaStreamSynchronize(streams[i]);
         if (e != cudaSuccess && rc == RT_OK) rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: %s", cudaGetErrorString(e));
-        cudaStreamDestroy(streams[i]);
     }
     return rc;
 }
