@@ -130,8 +130,11 @@ struct LaneQueue {
 // QUEUED = postpone triangle tests through the per-lane queue (incoherent batches); otherwise the
 // triangles of a hit leaf slot are tested inside the node step (coherent batches: neighbouring
 // lanes reach their leaves in the same step anyway, and the nearest hit shrinks tmax earlier).
+#ifndef RT_TRACE_MIN_BLOCKS
+#define RT_TRACE_MIN_BLOCKS 7
+#endif
 template <int MODE, bool STATS, bool QUEUED>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ TraceParams p) {
     using S = typename std::conditional<STATS, Stats, NoStats>::type;
     using Vis = typename VisitorOf<MODE, S>::type;
     __shared__ uint32_t s_queue[QUEUED ? kQueueCap : 1][kTraceThreads];

@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(unit: str) -> str:
         obj = os.path.join(objdir, unit.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, unit), "-o", obj]
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("TRIRO_NVCC_EXTRA", "").split(), "-I", INCLUDE, "-c",
+               os.path.join(CSRC, unit), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
