@@ -299,7 +299,7 @@ def run_b200(args):
                          "compulsory_bytes_per_ray": 12.0 + 26.0 + rmi.as_wrapper.header["used_bytes"] / n},
             "e2e": {"value": world * n * steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 12 * n + 12,
                     "d2h_bytes_per_step": 26 * n, "api": "rt_host_trace_closest (pinned host buffers, ramped chunks up to 2 Mi rays on 3 streams)"},
-            "gpu_launches": steps, "clocks": clk.summary(),
+            "gpu_launches": steps * world, "clocks": clk.summary(),
         }
         if bcast_ms is not None:
             line["bvh_build_plus_broadcast_ms"] = bcast_ms

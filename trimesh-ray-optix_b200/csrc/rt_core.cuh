@@ -260,6 +260,36 @@ RT_HD uint32_t spread3(uint32_t x) {   // bit i (0..7) -> bit 3i
     return x;
 }
 
+// hm8 (slot hit mask) -> Ylitie hit mask: inner hits moved to priority position (slot ^ octinv) in
+// bits 24..31, triangle bits (3 per slot) masked by trimask in bits 0..23.
+RT_HD uint32_t permute_by_octant(uint32_t in8, uint32_t octinv) {   // three conditional delta swaps
+    const uint32_t m1 = (octinv & 1u) ? 0x55u : 0u, m2 = (octinv & 2u) ? 0x33u : 0u, m4 = (octinv & 4u) ? 0x0fu : 0u;
+    uint32_t t;
+    t = ((in8 >> 1) ^ in8) & m1; in8 ^= t | (t << 1);
+    t = ((in8 >> 2) ^ in8) & m2; in8 ^= t | (t << 2);
+    t = ((in8 >> 4) ^ in8) & m4; in8 ^= t | (t << 4);
+    return in8;
+}
+#if defined(__CUDACC__) && defined(RT_MASK_LUT)
+// Shared-memory lookup tables for the two bit permutations: ~30 ALU-pipe instructions per node
+// become two LDS (the ALU pipe is the traversal kernel's bottleneck, the LSU pipe is idle).
+__shared__ uint32_t g_lut_spread7[256];     // spread3(x) * 7
+__shared__ uint8_t g_lut_perm[8][256];      // permute_by_octant(x, o)
+__device__ __forceinline__ void init_mask_luts() {
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) g_lut_spread7[i] = spread3(i) * 7u;
+    for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) g_lut_perm[i >> 8][i & 255u] = (uint8_t)permute_by_octant(i & 255u, i >> 8);
+    __syncthreads();
+}
+#endif
+RT_HD uint32_t finish_masks(uint32_t hm8, uint32_t imask, uint32_t trimask, uint32_t octinv) {
+#if defined(__CUDA_ARCH__) && defined(RT_MASK_LUT)
+    const uint32_t in8 = g_lut_perm[octinv][hm8 & imask];
+    return (in8 << 24) | (g_lut_spread7[hm8] & trimask);
+#else
+    return (permute_by_octant(hm8 & imask, octinv) << 24) | ((spread3(hm8) * 7u) & trimask);
+#endif
+}
+
 RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
                          float tmin, float tmax) {
     const float px = as_float(n0.x), py = as_float(n0.y), pz = as_float(n0.z);
@@ -305,18 +335,7 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
 #undef RT_SLAB
     }
     const uint32_t hm8 = ~miss & 0xffu;
-    const uint32_t imask = n0.w >> 24;
-    // inner hits: move slot s to priority position s ^ octinv (three conditional delta swaps)
-    uint32_t in8 = hm8 & imask;
-    {
-        const uint32_t m1 = (r.octinv & 1u) ? 0x55u : 0u, m2 = (r.octinv & 2u) ? 0x33u : 0u, m4 = (r.octinv & 4u) ? 0x0fu : 0u;
-        uint32_t t;
-        t = ((in8 >> 1) ^ in8) & m1; in8 ^= t | (t << 1);
-        t = ((in8 >> 2) ^ in8) & m2; in8 ^= t | (t << 2);
-        t = ((in8 >> 4) ^ in8) & m4; in8 ^= t | (t << 4);
-    }
-    const uint32_t tri24 = (spread3(hm8) * 7u) & n1.z;
-    return (in8 << 24) | tri24;
+    return finish_masks(hm8, n0.w >> 24, n1.z, r.octinv);
 }
 
 }  // namespace rt

@@ -12,6 +12,7 @@
 // from a global ray counter with one warp-aggregated atomic (Aila & Laine 2009).
 #include <stdlib.h>
 #include <type_traits>
+#define RT_MASK_LUT 1
 #include "rt_api.h"
 #include "rt_traverse.cuh"
 
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
     using S = typename std::conditional<STATS, Stats, NoStats>::type;
     using Vis = typename VisitorOf<MODE, S>::type;
     __shared__ uint32_t s_queue[QUEUED ? kQueueCap : 1][kTraceThreads];
+    init_mask_luts();
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
     const uint8_t* tris = p.blob + hdr->tris_offset;
     const uint8_t* nodes = p.blob + hdr->nodes_offset;
