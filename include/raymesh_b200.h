@@ -80,7 +80,10 @@ typedef struct rt_blob_header {
     uint64_t used_bytes;    /* prefix of the blob that must travel (NCCL broadcast / save) */
     float aabb_lo[3];
     float aabb_hi[3];
-    uint32_t reserved[44];
+    uint32_t bad_index_faces;  /* faces whose vertex indices were out of range (build error) */
+    uint32_t node_overflow;    /* node pool overflow (internal error, must be 0) */
+    uint64_t parents_offset;   /* byte offset of the per-node (parent << 3 | slot) array used by rt_bvh_refit */
+    uint32_t reserved[40];
 } rt_blob_header;
 
 /* Size of the scratch buffer every trace call needs (zeroed by the call itself). */
@@ -99,6 +102,14 @@ int rt_bvh_build(const float* vertices, int64_t n_verts,   /* [n_verts,3] f32 co
                  const int32_t* faces, int64_t n_faces,    /* [n_faces,3] i32 contiguous */
                  void* workspace, size_t workspace_bytes,
                  void* blob, size_t blob_bytes, void* stream);
+/* Same topology, new vertex positions: rewrites the triangle records and re-fits every node box
+ * bottom-up in the existing blob (the reference rebuilds from scratch in
+ * update_raw, ray_optix.py:55-69).  `blob` must be the complete blob rt_bvh_build produced (not just
+ * its used prefix).  workspace: rt_bvh_refit_sizes() bytes. */
+int rt_bvh_refit_sizes(int64_t n_faces, size_t* workspace_bytes);
+int rt_bvh_refit(const float* vertices, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                 void* workspace, size_t workspace_bytes, void* blob, size_t blob_bytes, void* stream);
+
 /* ---- Radix sort exposed for testing (the builder's onesweep sort, 64-bit key + 32-bit value). */
 int rt_sort_sizes(int64_t n, size_t* workspace_bytes);
 int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, int64_t n, void* workspace, size_t workspace_bytes,

@@ -20,13 +20,14 @@ using namespace rt;
 
 namespace {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-struct Layout { size_t tris_offset, nodes_offset, total; uint32_t node_cap; };
+struct Layout { size_t tris_offset, nodes_offset, parents_offset, total; uint32_t node_cap; };
 Layout layout(int64_t n) {
     Layout l;
     l.tris_offset = RT_BLOB_HEADER_BYTES;
     l.nodes_offset = align_up(l.tris_offset + (size_t)n * 48u, 256);
     l.node_cap = (uint32_t)(n / 3 + 2);
-    l.total = l.nodes_offset + (size_t)l.node_cap * 80u;
+    l.parents_offset = align_up(l.nodes_offset + (size_t)l.node_cap * 80u, 256);
+    l.total = l.parents_offset + align_up((size_t)l.node_cap * 4u, 256);
     return l;
 }
 struct VecStack {
@@ -53,7 +54,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     rt_blob_header h;
     memset(&h, 0, sizeof(h));
     h.magic = RT_BLOB_MAGIC; h.abi_version = RT_ABI_VERSION; h.n_tris = (uint32_t)n; h.n_nodes_cap = lay.node_cap;
-    h.tris_offset = lay.tris_offset; h.nodes_offset = lay.nodes_offset;
+    h.tris_offset = lay.tris_offset; h.nodes_offset = lay.nodes_offset; h.parents_offset = lay.parents_offset;
     if (n == 0) {
         Node8 nd; memset(&nd, 0, sizeof(nd)); nd.ex = nd.ey = nd.ez = 1;
         memcpy(blob + lay.nodes_offset, &nd, 80);
@@ -109,6 +110,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     t.box = box.data(); t.sorted_prim = vals.data();
     CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
+    o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
     uint32_t begin = 0, end = 1, depth = 0;
     while (begin < end) {
         for (uint32_t w = begin; w < end; ++w) collapse_node(t, o, w, verts, nv, faces);
@@ -118,8 +120,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     }
     h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
     for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
-    h.reserved[1] = node_count > lay.node_cap ? 1u : 0u;
-    h.reserved[2] = tri_count;
+    h.node_overflow = node_count > lay.node_cap ? 1u : 0u;
     memcpy(blob, &h, sizeof(h));
     return 0;
 }
@@ -242,7 +243,7 @@ extern "C" int hs_check_blob(const uint8_t* blob, size_t blob_bytes, uint64_t* i
     rt_blob_header h; memcpy(&h, blob, sizeof(h));
     if (h.magic != RT_BLOB_MAGIC || h.abi_version != RT_ABI_VERSION) return 101;
     if (h.used_bytes > blob_bytes || h.nodes_offset + (uint64_t)h.n_nodes * 80u > blob_bytes) return 102;
-    if (h.reserved[0] != 0 || h.reserved[1] != 0) return 103;
+    if (h.bad_index_faces != 0 || h.node_overflow != 0) return 103;
     Checker c; c.nodes = blob + h.nodes_offset; c.tris = blob + h.tris_offset; c.n_nodes = h.n_nodes; c.n_tris = h.n_tris;
     c.node_seen.assign(h.n_nodes, 0); c.tri_seen.assign(h.n_tris, 0);
     c.walk(0, 0);
@@ -258,5 +259,40 @@ extern "C" int hs_check_blob(const uint8_t* blob, size_t blob_bytes, uint64_t* i
 extern "C" int hs_blob_prims(const uint8_t* blob, int32_t* prims_out) {
     rt_blob_header h; memcpy(&h, blob, sizeof(h));
     for (uint32_t i = 0; i < h.n_tris; ++i) memcpy(&prims_out[i], blob + h.tris_offset + (size_t)i * 48u + 12, 4);
+    return 0;
+}
+
+// Refit with new vertex positions (same faces): sequential version of k_refit_tris / k_refit_nodes.
+extern "C" int hs_refit(const float* verts, int64_t nv, const int32_t* faces, int64_t n, uint8_t* blob, size_t blob_bytes) {
+    rt_blob_header h; memcpy(&h, blob, sizeof(h));
+    if (h.magic != RT_BLOB_MAGIC || h.n_tris != (uint32_t)n) return -4;
+    if (h.parents_offset + (uint64_t)h.n_nodes * 4u > blob_bytes) return -3;
+    if (n == 0) return 0;
+    uint8_t* tris = blob + h.tris_offset;
+    uint8_t* nodes = blob + h.nodes_offset;
+    const uint32_t* parent = reinterpret_cast<const uint32_t*>(blob + h.parents_offset);
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t prim; memcpy(&prim, tris + (size_t)i * 48u + 12, 4);
+        write_tri_record(tris, (uint32_t)i, (uint32_t)prim, verts, nv, faces);
+    }
+    std::vector<BBox> node_box(h.n_nodes);
+    std::vector<uint32_t> counters(h.n_nodes, 0);
+    for (uint32_t w0 = 0; w0 < h.n_nodes; ++w0) {
+        if (nodes[(size_t)w0 * 80u + 15] != 0) continue;
+        uint32_t w = w0;
+        for (;;) {
+            node_box[w] = refit_node(nodes, tris, w, node_box.data());
+            if (w == 0) {
+                h.aabb_lo[0] = node_box[0].lx; h.aabb_lo[1] = node_box[0].ly; h.aabb_lo[2] = node_box[0].lz;
+                h.aabb_hi[0] = node_box[0].hx; h.aabb_hi[1] = node_box[0].hy; h.aabb_hi[2] = node_box[0].hz;
+                break;
+            }
+            const uint32_t pw = parent[w] >> 3;
+            const uint32_t need = (uint32_t)__builtin_popcount((uint32_t)nodes[(size_t)pw * 80u + 15]);
+            if (++counters[pw] != need) break;
+            w = pw;
+        }
+    }
+    memcpy(blob, &h, sizeof(h));
     return 0;
 }

@@ -37,6 +37,7 @@ def lib():
         _LIB.hs_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 10
         _LIB.hs_check_blob.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         _LIB.hs_blob_prims.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.hs_refit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t]
     return _LIB
 
 
@@ -52,6 +53,16 @@ def build_blob(vertices, faces) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"hs_build failed: {rc}")
     return blob
+
+
+def refit_blob(blob: np.ndarray, vertices, faces) -> np.ndarray:
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+    out = np.ascontiguousarray(blob).copy()
+    rc = lib().hs_refit(_p(v), len(v), _p(f), len(f), _p(out), out.nbytes)
+    if rc != 0:
+        raise RuntimeError(f"hs_refit failed: {rc}")
+    return out
 
 
 def check_blob(blob: np.ndarray):

@@ -513,3 +513,67 @@ def test_golden_fixture_from_reference_host_logic(cuda_device):
     rs = make(g["sph_v"], g["sph_f"])
     torch.manual_seed(99)
     assert_bits_equal(rs.contains_points(torch.from_numpy(g["sph_pts"]).to(cuda_device)).cpu().numpy(), g["sph_default"], "sphere")
+
+
+# ---------------------------------------------------------------- refit and blob serialisation
+def test_refit_matches_rebuild_and_oracle(cuda_device):
+    v, f = synth.icosphere(5)
+    r = make(v, f)
+    rng = np.random.default_rng(3)
+    v2 = (v * np.array([1.2, 0.7, 1.1], np.float32) + rng.normal(0, 0.004, size=v.shape).astype(np.float32)).astype(np.float32)
+    r.refit(torch.from_numpy(v2))
+    blob = r.as_wrapper.blob.cpu().numpy()
+    assert hostsim.check_blob(blob)[0] == 0
+    o, d = synth.random_rays(60_000, seed=12, device=cuda_device, box=True)
+    o = o * 1.5
+    got = closest_to_numpy(r.intersects_closest(o, d))
+    om = oracle.OracleMesh(v2, f)
+    check_closest_vs_mirror(got, om, flat(o), flat(d))
+    fresh = make(v2, f)
+    ref = closest_to_numpy(fresh.intersects_closest(o, d))
+    for k in got:
+        assert_bits_equal(got[k], ref[k], f"refit vs rebuild {k}")
+    assert torch.equal(r.intersects_count(o, d), fresh.intersects_count(o, d))
+    assert torch.allclose(r.mesh_aabb[1], fresh.mesh_aabb[1])
+    with pytest.raises(ValueError):
+        r.as_wrapper._inner.refit(r.mesh_vertices, r.mesh_faces[:-1])
+
+
+def test_blob_save_load_roundtrip(cuda_device, tmp_path):
+    v, f = synth.icosphere(4)
+    r = make(v, f)
+    path = str(tmp_path / "bvh.pt")
+    r.save_bvh(path)
+    acc = hops.AccelStructure().load(path, device=cuda_device)
+    o, d = synth.random_rays(20_000, seed=2, device=cuda_device, box=True)
+    a = hops.intersects_closest(r.as_wrapper, o, d)
+    b = hops.intersects_closest(acc, o, d)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_numpy_adapter_follows_trimesh_ray_conventions(cuda_device):
+    """the call the reference benchmarks against, mesh.ray.intersects_location(o, d,
+    multiple_hits=False) with numpy float64 in / numpy out (test/performance_test.py:75)."""
+    from types import SimpleNamespace
+
+    from triro.ray.ray_numpy import RayMeshIntersector as NumpyRMI
+
+    v, f = synth.icosphere(3)
+    mesh = SimpleNamespace(vertices=v.astype(np.float64), faces=f.astype(np.int64))
+    ray = NumpyRMI(mesh)
+    o, d = synth.random_rays(5000, seed=6, box=True)
+    o64, d64 = (o * 2).numpy().astype(np.float64), d.numpy().astype(np.float64)
+    loc, index_ray, index_tri = ray.intersects_location(o64, d64, multiple_hits=False)
+    assert loc.dtype == np.float64 and index_ray.dtype == np.int64 and index_tri.dtype == np.int64
+    r = make(v, f)
+    hit, _, tri, tloc, _ = r.intersects_closest((o * 2).to(cuda_device), d.to(cuda_device))
+    assert np.array_equal(index_ray, np.nonzero(hit.cpu().numpy())[0]) and np.array_equal(index_tri, tri[hit].cpu().numpy())
+    assert np.allclose(loc, tloc[hit].cpu().numpy())
+    loc_m, ray_m, tri_m = ray.intersects_location(o64, d64)
+    assert len(loc_m) == int(r.intersects_count((o * 2).to(cuda_device), d.to(cuda_device)).clamp(max=8).sum())
+    assert np.array_equal(ray.intersects_first(o64, d64), tri.cpu().numpy()) and ray.intersects_first(o64, d64).dtype == np.int64
+    assert np.array_equal(ray.intersects_any(o64, d64), hit.cpu().numpy())
+    t2, r2 = ray.intersects_id(o64, d64, multiple_hits=False)
+    assert np.array_equal(t2, index_tri) and np.array_equal(r2, index_ray)
+    assert ray.contains_points(np.array([[0, 0, 0.999], [0, 0, 1.5]])).tolist() == [True, False]

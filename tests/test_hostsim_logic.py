@@ -102,3 +102,28 @@ def test_empty_mesh_and_nan_rays():
     blob = hostsim.build_blob(v, f)
     d2 = np.array([[0, 0, 0], [0, 0, -1]], np.float32)
     assert hostsim.trace(blob, "count", o, d2)["count"].tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("name", ["tri2", "tri9", "ico3", "soup", "hf"])
+def test_refit_keeps_the_blob_conservative_and_results_exact(name):
+    """Refit path: deform the vertices, re-fit in place, compare with the oracle on the new mesh."""
+    v, f = mesh(name)
+    blob = hostsim.build_blob(v, f)
+    rng = np.random.default_rng(1)
+    v2 = (v * np.array([1.3, 0.8, 1.1], np.float32) + rng.normal(0, 0.02, size=v.shape).astype(np.float32) + np.float32(0.1)).astype(np.float32)
+    blob2 = hostsim.refit_blob(blob, v2, f)
+    code, info = hostsim.check_blob(blob2)
+    assert code == 0, f"hs_check_blob after refit -> {code}"
+    o, d = synth.random_rays(3000, seed=5, box=True)
+    o, d = (o * 1.6).numpy(), d.numpy()
+    ref = oracle.query(oracle.OracleMesh(v2, f, use_bvh=False), o, d, oracle.MIRROR)
+    got = hostsim.trace(blob2, "closest", o, d)
+    for k in ("hit", "front", "tri"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["loc"].view(np.uint32), ref["loc"].view(np.uint32))
+    assert np.array_equal(hostsim.trace(blob2, "count", o, d)["count"], ref["count"])
+    # refit with the original vertices reproduces the original boxes' answers
+    blob3 = hostsim.refit_blob(blob2, v, f)
+    assert hostsim.check_blob(blob3)[0] == 0
+    ref0 = oracle.query(oracle.OracleMesh(v, f, use_bvh=False), o, d, oracle.MIRROR)
+    assert np.array_equal(hostsim.trace(blob3, "closest", o, d)["tri"], ref0["tri"])

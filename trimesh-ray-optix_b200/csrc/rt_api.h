@@ -34,7 +34,7 @@ inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Blob geometry derived from the triangle count alone (host side, no device read needed).
 struct BlobLayout {
-    size_t tris_offset, nodes_offset, total_bytes;
+    size_t tris_offset, nodes_offset, parents_offset, total_bytes;
     uint32_t node_cap;
 };
 inline BlobLayout blob_layout(int64_t n_faces) {
@@ -43,7 +43,8 @@ inline BlobLayout blob_layout(int64_t n_faces) {
     l.nodes_offset = align_up_sz(l.tris_offset + (size_t)(n_faces > 0 ? n_faces : 0) * 48u, 256);
     // wide nodes <= n/3 + 2 (every bottom node holds > 3 triangles, every upper node has 8 children)
     l.node_cap = (uint32_t)((n_faces > 0 ? n_faces : 0) / 3 + 2);
-    l.total_bytes = l.nodes_offset + (size_t)l.node_cap * 80u;
+    l.parents_offset = align_up_sz(l.nodes_offset + (size_t)l.node_cap * 80u, 256);
+    l.total_bytes = l.parents_offset + align_up_sz((size_t)l.node_cap * 4u, 256);
     return l;
 }
 

@@ -263,8 +263,9 @@ __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n,
         h.aabb_lo[a] = n > 0 ? ord2f(st->bounds_lo[a]) : 0.0f;
         h.aabb_hi[a] = n > 0 ? ord2f(st->bounds_hi[a]) : 0.0f;
     }
-    h.reserved[0] = n > 0 ? st->bad_index : 0u;                          // faces with out-of-range indices
-    h.reserved[1] = n > 0 ? (st->node_count > lay.node_cap ? 1u : 0u) : 0u;  // node pool overflow (must not happen)
+    h.bad_index_faces = n > 0 ? st->bad_index : 0u;
+    h.node_overflow = n > 0 ? (st->node_count > lay.node_cap ? 1u : 0u) : 0u;   // must not happen
+    h.parents_offset = lay.parents_offset;
     *hdr = h;
     if (n == 0) {
         // empty mesh: a root without children, every ray misses
@@ -272,6 +273,7 @@ __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n,
         memset(&nd, 0, sizeof(nd));
         nd.ex = nd.ey = nd.ez = 1;   // imask = trimask = 0: no slot is ever reported
         *reinterpret_cast<Node8*>(reinterpret_cast<uint8_t*>(hdr) + lay.nodes_offset) = nd;
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(hdr) + lay.parents_offset) = 0xffffffffu;
     }
 }
 
@@ -344,6 +346,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         t.sorted_prim = w.vals;
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
+        o.parent = reinterpret_cast<uint32_t*>(blob8 + lay.parents_offset);
         o.node_count = &w.state->node_count; o.tri_count = &w.state->tri_count; o.node_cap = lay.node_cap;
         int per_sm = 0;
         RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse, 128, 0));
@@ -356,6 +359,95 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         RT_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(cgrid), dim3(128), args, 0, stream));
     }
     k_finalize<<<1, 32, 0, stream>>>(hdr, w.state, n, lay);
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ refit (same topology, new vertices)
+namespace rt {
+struct RefitWorkspace {
+    BBox* node_box;        // [node_cap]
+    uint32_t* counters;    // [node_cap] children that have reported
+    size_t total;
+};
+static RefitWorkspace carve_refit(void* base, uint32_t node_cap) {
+    RefitWorkspace w;
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    const size_t cb = align_up_sz((size_t)node_cap * 4u, 256);
+    w.counters = reinterpret_cast<uint32_t*>(p);
+    w.node_box = reinterpret_cast<BBox*>(p ? p + cb : nullptr);
+    w.total = cb + align_up_sz((size_t)node_cap * sizeof(BBox), 256);
+    return w;
+}
+
+__global__ void __launch_bounds__(256) k_refit_tris(const float* __restrict__ verts, int64_t nv,
+                                                    const int32_t* __restrict__ faces, int64_t n, uint8_t* tris) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t prim = *reinterpret_cast<const int32_t*>(tris + (size_t)i * 48u + 12);
+        write_tri_record(tris, (uint32_t)i, (uint32_t)prim, verts, nv, faces);
+    }
+}
+
+// one thread per node without inner children starts; the last child to report climbs to the parent
+__global__ void __launch_bounds__(128) k_refit_nodes(rt_blob_header* hdr, BBox* node_box, uint32_t* counters) {
+    uint8_t* blob = reinterpret_cast<uint8_t*>(hdr);
+    uint8_t* nodes = blob + hdr->nodes_offset;
+    const uint8_t* tris = blob + hdr->tris_offset;
+    const uint32_t* parent = reinterpret_cast<const uint32_t*>(blob + hdr->parents_offset);
+    const uint32_t n_nodes = hdr->n_nodes;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t w0 = blockIdx.x * blockDim.x + threadIdx.x; w0 < n_nodes; w0 += stride) {
+        if (nodes[(size_t)w0 * 80u + 15] != 0) continue;   // imask != 0: an inner child will take care of it
+        uint32_t w = w0;
+        for (;;) {
+            const BBox nb = refit_node(nodes, tris, w, node_box);
+            __stcg(reinterpret_cast<float4*>(&node_box[w]), make_float4(nb.lx, nb.ly, nb.lz, 0.f));
+            __stcg(reinterpret_cast<float4*>(&node_box[w]) + 1, make_float4(nb.hx, nb.hy, nb.hz, 0.f));
+            if (w == 0u) {
+                hdr->aabb_lo[0] = nb.lx; hdr->aabb_lo[1] = nb.ly; hdr->aabb_lo[2] = nb.lz;
+                hdr->aabb_hi[0] = nb.hx; hdr->aabb_hi[1] = nb.hy; hdr->aabb_hi[2] = nb.hz;
+                break;
+            }
+            const uint32_t pw = parent[w] >> 3;
+            const uint32_t need = (uint32_t)__popc((uint32_t)nodes[(size_t)pw * 80u + 15]);
+            __threadfence();
+            if (atomicAdd(&counters[pw], 1u) + 1u != need) break;
+            w = pw;
+        }
+    }
+}
+}  // namespace rt
+
+extern "C" int rt_bvh_refit_sizes(int64_t n_faces, size_t* workspace_bytes) {
+    RT_REQUIRE(n_faces >= 0 && n_faces <= (int64_t)1 << 30 && workspace_bytes, RT_ERR_INVALID, "rt_bvh_refit_sizes: bad arguments");
+    *workspace_bytes = carve_refit(nullptr, blob_layout(n_faces).node_cap).total;
+    return RT_OK;
+}
+
+extern "C" int rt_bvh_refit(const float* vertices, int64_t n_verts, const int32_t* faces, int64_t n_faces, void* workspace,
+                            size_t workspace_bytes, void* blob, size_t blob_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    RT_REQUIRE(n_verts >= 0 && n_faces >= 0 && n_faces <= (int64_t)1 << 30, RT_ERR_INVALID, "rt_bvh_refit: bad sizes");
+    RT_REQUIRE(blob && workspace, RT_ERR_INVALID, "rt_bvh_refit: null blob/workspace");
+    RT_REQUIRE(((uintptr_t)blob & 255) == 0 && ((uintptr_t)workspace & 255) == 0, RT_ERR_INVALID,
+               "rt_bvh_refit: blob and workspace must be 256-byte aligned");
+    const BlobLayout lay = blob_layout(n_faces);
+    RT_REQUIRE(blob_bytes >= lay.total_bytes, RT_ERR_SIZE,
+               "rt_bvh_refit: blob %zu < %zu (refit needs the complete blob of rt_bvh_build, not its used prefix)", blob_bytes,
+               lay.total_bytes);
+    RefitWorkspace w = carve_refit(workspace, lay.node_cap);
+    RT_REQUIRE(workspace_bytes >= w.total, RT_ERR_SIZE, "rt_bvh_refit: workspace %zu < %zu", workspace_bytes, w.total);
+    if (n_faces == 0) return RT_OK;
+    RT_REQUIRE(vertices && faces && n_verts > 0, RT_ERR_INVALID, "rt_bvh_refit: null vertices/faces");
+    DeviceInfo dev;
+    RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "rt_bvh_refit: no CUDA device");
+    uint8_t* blob8 = reinterpret_cast<uint8_t*>(blob);
+    RT_CUDA_TRY(cudaMemsetAsync(w.counters, 0, align_up_sz((size_t)lay.node_cap * 4u, 256), stream));
+    k_refit_tris<<<grid_for(n_faces, 256, dev.sm_count, 8), 256, 0, stream>>>(vertices, n_verts, faces, n_faces,
+                                                                              blob8 + lay.tris_offset);
+    k_refit_nodes<<<grid_for(lay.node_cap, 128, dev.sm_count, 8), 128, 0, stream>>>(reinterpret_cast<rt_blob_header*>(blob8),
+                                                                                    w.node_box, w.counters);
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }

@@ -145,6 +145,17 @@ RT_HD uint32_t load_cg_u32(const uint32_t* p) { return __ldcg(p); }
 RT_HD uint32_t load_cg_u32(const uint32_t* p) { return *p; }
 #endif
 
+#if defined(__CUDA_ARCH__)
+RT_HD BBox load_box(const BBox* p) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    BBox r; r.lx = a.x; r.ly = a.y; r.lz = a.z; r.pad0 = 0.f; r.hx = b.x; r.hy = b.y; r.hz = b.z; r.pad1 = 0.f;
+    return r;
+}
+#else
+RT_HD BBox load_box(const BBox* p) { return *p; }
+#endif
+
 RT_HD float exp2_biased(uint32_t e) { return as_float(e << 23); }
 
 // Smallest biased exponent e (1..254) with 255 * 2^(e-127) >= ext.
@@ -163,6 +174,7 @@ struct CollapseOut {
     uint8_t* nodes;          // Node8 array (80 B each)
     uint8_t* tris;           // TriRecord array (48 B each)
     uint32_t* wide_src;      // binary reference expanded by each wide node
+    uint32_t* parent;        // (parent node << 3) | slot of each wide node, 0xffffffff for the root (refit)
     uint32_t* node_count;    // atomic allocators
     uint32_t* tri_count;
     uint32_t node_cap;
@@ -173,6 +185,106 @@ struct CollapseOut {
 // still expandable (an inner node covering more than kLeafMaxTris triangles) by its own two
 // children until there are 8 children.  Subtrees with <= kLeafMaxTris triangles become leaf
 // slots (their triangles are contiguous in Morton order).
+// Quantisation of the child boxes of one wide node: frame (p, 2^e) from the node box, 8-bit planes
+// rounded outwards and verified in binary64 against the exact decode p + q * 2^e.  Shared by the
+// builder (collapse) and the refit path.  Absent slots get an inverted box.
+RT_HD void quantise_slots(const BBox& nb, const BBox slot_box[8], uint32_t present, Node8& nd) {
+    const float p[3] = {nb.lx, nb.ly, nb.lz};
+    const float hi3[3] = {nb.hx, nb.hy, nb.hz};
+    uint32_t e[3];
+    for (int a = 0; a < 3; ++a) {
+        e[a] = quant_exponent(hi3[a] - p[a]);
+        // make sure every child's upper plane is representable (<= 255 steps)
+        for (;;) {
+            const double sc = (double)exp2_biased(e[a]);
+            bool ok = true;
+            for (int s = 0; s < 8; ++s) {
+                if (!((present >> s) & 1u)) continue;
+                const float ch = a == 0 ? slot_box[s].hx : (a == 1 ? slot_box[s].hy : slot_box[s].hz);
+                if ((double)p[a] + 255.0 * sc < (double)ch) { ok = false; break; }
+            }
+            if (ok || e[a] >= 254u) break;
+            ++e[a];
+        }
+    }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2];
+    for (int s = 0; s < 8; ++s) {
+        if (!((present >> s) & 1u)) {
+            nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;   // inverted box: never hit
+            nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+            continue;
+        }
+        uint8_t ql[3], qh[3];
+        for (int a = 0; a < 3; ++a) {
+            const float cl = a == 0 ? slot_box[s].lx : (a == 1 ? slot_box[s].ly : slot_box[s].lz);
+            const float ch = a == 0 ? slot_box[s].hx : (a == 1 ? slot_box[s].hy : slot_box[s].hz);
+            const double sc = (double)exp2_biased(e[a]);
+            double fl = floor(((double)cl - (double)p[a]) / sc);
+            if (!(fl >= 0.0)) fl = 0.0;
+            if (fl > 255.0) fl = 255.0;
+            while (fl > 0.0 && (double)p[a] + fl * sc > (double)cl) fl -= 1.0;
+            double fh = ceil(((double)ch - (double)p[a]) / sc);
+            if (!(fh >= 0.0)) fh = 0.0;
+            if (fh > 255.0) fh = 255.0;
+            while (fh < 255.0 && (double)p[a] + fh * sc < (double)ch) fh += 1.0;
+            ql[a] = (uint8_t)fl; qh[a] = (uint8_t)fh;
+        }
+        nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
+        nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
+    }
+}
+
+RT_HD int32_t clamp_index(int32_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? (int32_t)(n - 1) : i); }
+
+// 48-byte triangle record `slot` <- vertices of face `prim`
+RT_HD void write_tri_record(uint8_t* tris, uint32_t slot, uint32_t prim, const float* __restrict__ verts, int64_t n_verts,
+                            const int32_t* __restrict__ faces) {
+    const int32_t i0 = clamp_index(faces[3 * (size_t)prim], n_verts), i1 = clamp_index(faces[3 * (size_t)prim + 1], n_verts),
+                  i2 = clamp_index(faces[3 * (size_t)prim + 2], n_verts);
+    TriRecord tr;
+    tr.v0x = verts[3 * (size_t)i0]; tr.v0y = verts[3 * (size_t)i0 + 1]; tr.v0z = verts[3 * (size_t)i0 + 2];
+    tr.v1x = verts[3 * (size_t)i1]; tr.v1y = verts[3 * (size_t)i1 + 1]; tr.v1z = verts[3 * (size_t)i1 + 2];
+    tr.v2x = verts[3 * (size_t)i2]; tr.v2y = verts[3 * (size_t)i2 + 1]; tr.v2z = verts[3 * (size_t)i2 + 2];
+    tr.prim = (int32_t)prim; tr.pad1 = 0; tr.pad2 = 0;
+    *reinterpret_cast<TriRecord*>(tris + (size_t)slot * 48u) = tr;
+}
+
+// Bottom-up update of one wide node after its children are final (refit): recomputes the slot
+// boxes (leaf slots from their triangle records, inner slots from child_box[]), re-quantises and
+// returns the node's own box.  Topology fields are untouched.
+RT_HD BBox refit_node(uint8_t* nodes, const uint8_t* tris, uint32_t w, const BBox* child_box_of_node) {
+    Node8 nd = *reinterpret_cast<const Node8*>(nodes + (size_t)w * 80u);
+    BBox slot_box[8];
+    BBox nb; nb.lx = nb.ly = nb.lz = INFINITY; nb.hx = nb.hy = nb.hz = -INFINITY; nb.pad0 = nb.pad1 = 0.f;
+    uint32_t present = 0, rel = 0, toff = 0;
+    for (int s = 0; s < 8; ++s) {
+        const bool inner = (nd.imask >> s) & 1u;
+        const uint32_t un = (nd.trimask >> (3 * s)) & 7u;
+        if (inner) {
+            slot_box[s] = load_box(child_box_of_node + nd.child_base + rel);
+            ++rel;
+        } else if (un) {
+            const uint32_t cnt = un == 1u ? 1u : (un == 3u ? 2u : 3u);
+            BBox b; b.lx = b.ly = b.lz = INFINITY; b.hx = b.hy = b.hz = -INFINITY; b.pad0 = b.pad1 = 0.f;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const float* tp = reinterpret_cast<const float*>(tris + (size_t)(nd.tri_base + toff + j) * 48u);
+                b = bbox_union(b, tri_bbox(tp[0], tp[1], tp[2], tp[4], tp[5], tp[6], tp[8], tp[9], tp[10]));
+            }
+            toff += cnt;
+            slot_box[s] = b;
+        } else {
+            continue;
+        }
+        present |= 1u << s;
+        nb = bbox_union(nb, slot_box[s]);
+    }
+    if (present == 0u) { nb.lx = nb.ly = nb.lz = 0.f; nb.hx = nb.hy = nb.hz = 0.f; }
+    quantise_slots(nb, slot_box, present, nd);
+    *reinterpret_cast<Node8*>(nodes + (size_t)w * 80u) = nd;
+    return nb;
+}
+
 RT_HD bool bt_expandable(const BinaryTree& t, uint32_t ref) {
     return ref < (uint32_t)(t.n - 1) && bt_count(t, ref) > (uint32_t)kLeafMaxTris;
 }
@@ -180,8 +292,6 @@ RT_HD float bt_area(const BinaryTree& t, uint32_t ref) {
     const float a = bbox_half_area(t.box[ref]);
     return a >= 0.0f ? a : 0.0f;   // NaN / negative -> 0
 }
-RT_HD int32_t clamp_index(int32_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? (int32_t)(n - 1) : i); }
-
 RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, const float* __restrict__ verts,
                          int64_t n_verts, const int32_t* __restrict__ faces) {
     uint32_t ref[8];
@@ -247,75 +357,32 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     const uint32_t child_base = n_inner ? atomic_add_u32(o.node_count, n_inner) : 0u;
     const uint32_t tri_base = n_tris ? atomic_add_u32(o.tri_count, n_tris) : 0u;
 
-    // quantisation frame
-    const float p[3] = {nb.lx, nb.ly, nb.lz};
-    const float hi3[3] = {nb.hx, nb.hy, nb.hz};
-    uint32_t e[3];
-    for (int a = 0; a < 3; ++a) {
-        e[a] = quant_exponent(hi3[a] - p[a]);
-        // make sure every child's upper plane is representable (<= 255 steps)
-        for (;;) {
-            const double sc = (double)exp2_biased(e[a]);
-            bool ok = true;
-            for (int i = 0; i < k; ++i) {
-                const float ch = a == 0 ? cb[i].hx : (a == 1 ? cb[i].hy : cb[i].hz);
-                if ((double)p[a] + 255.0 * sc < (double)ch) { ok = false; break; }
-            }
-            if (ok || e[a] >= 254u) break;
-            ++e[a];
-        }
-    }
+    BBox slot_box[8];
+    uint32_t present = 0;
+    for (int s = 0; s < 8; ++s)
+        if (child_in_slot[s] >= 0) { slot_box[s] = cb[child_in_slot[s]]; present |= 1u << s; }
     Node8 nd;
-    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
-    nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2];
+    quantise_slots(nb, slot_box, present, nd);
     nd.child_base = child_base;
     nd.tri_base = tri_base;
     uint32_t imask = 0, trimask = 0, rel = 0, toff = 0;
     for (int s = 0; s < 8; ++s) {
         const int i = child_in_slot[s];
-        if (i < 0) {
-            nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;   // inverted box: never hit
-            nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
-            continue;
-        }
-        uint8_t ql[3], qh[3];
-        for (int a = 0; a < 3; ++a) {
-            const float cl = a == 0 ? cb[i].lx : (a == 1 ? cb[i].ly : cb[i].lz);
-            const float ch = a == 0 ? cb[i].hx : (a == 1 ? cb[i].hy : cb[i].hz);
-            const double sc = (double)exp2_biased(e[a]);
-            double fl = floor(((double)cl - (double)p[a]) / sc);
-            if (!(fl >= 0.0)) fl = 0.0;
-            if (fl > 255.0) fl = 255.0;
-            while (fl > 0.0 && (double)p[a] + fl * sc > (double)cl) fl -= 1.0;
-            double fh = ceil(((double)ch - (double)p[a]) / sc);
-            if (!(fh >= 0.0)) fh = 0.0;
-            if (fh > 255.0) fh = 255.0;
-            while (fh < 255.0 && (double)p[a] + fh * sc < (double)ch) fh += 1.0;
-            ql[a] = (uint8_t)fl; qh[a] = (uint8_t)fh;
-        }
-        nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
-        nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
+        if (i < 0) continue;
         if (inner[i]) {
             imask |= 1u << s;
-            if (child_base + rel < o.node_cap) o.wide_src[child_base + rel] = ref[i];
+            if (child_base + rel < o.node_cap) {
+                o.wide_src[child_base + rel] = ref[i];
+                o.parent[child_base + rel] = (w << 3) | (uint32_t)s;
+            }
             ++rel;
         } else {
             const uint32_t cnt = bt_count(t, ref[i]);
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             trimask |= unary << (3 * s);
             const uint32_t f0 = bt_first(t, ref[i]);
-            for (uint32_t j = 0; j < cnt; ++j) {
-                const uint32_t prim = t.sorted_prim[f0 + j];
-                const int32_t i0 = clamp_index(faces[3 * (size_t)prim], n_verts),
-                              i1 = clamp_index(faces[3 * (size_t)prim + 1], n_verts),
-                              i2 = clamp_index(faces[3 * (size_t)prim + 2], n_verts);
-                TriRecord tr;
-                tr.v0x = verts[3 * (size_t)i0]; tr.v0y = verts[3 * (size_t)i0 + 1]; tr.v0z = verts[3 * (size_t)i0 + 2];
-                tr.v1x = verts[3 * (size_t)i1]; tr.v1y = verts[3 * (size_t)i1 + 1]; tr.v1z = verts[3 * (size_t)i1 + 2];
-                tr.v2x = verts[3 * (size_t)i2]; tr.v2y = verts[3 * (size_t)i2 + 1]; tr.v2z = verts[3 * (size_t)i2 + 2];
-                tr.prim = (int32_t)prim; tr.pad1 = 0; tr.pad2 = 0;
-                *reinterpret_cast<TriRecord*>(o.tris + (size_t)(tri_base + toff + j) * 48u) = tr;
-            }
+            for (uint32_t j = 0; j < cnt; ++j)
+                write_tri_record(o.tris, tri_base + toff + j, t.sorted_prim[f0 + j], verts, n_verts, faces);
             toff += cnt;
         }
     }
@@ -323,6 +390,7 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     nd.trimask = trimask;
     nd.reserved = 0;
     if (w < o.node_cap) *reinterpret_cast<Node8*>(o.nodes + (size_t)w * 80u) = nd;
+    if (w == 0) o.parent[0] = 0xffffffffu;
 }
 
 }  // namespace rt

@@ -54,6 +54,8 @@ def _declare(lib):
         "rt_device_sm_count": (ci, []),
         "rt_bvh_sizes": (ci, [i64, i64, psz, psz]),
         "rt_bvh_build": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
+        "rt_bvh_refit_sizes": (ci, [i64, psz]),
+        "rt_bvh_refit": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
         "rt_sort_sizes": (ci, [i64, psz]),
         "rt_sort_pairs_u64": (ci, [vp, vp, i64, vp, sz, vp]),
         "rt_trace_any": (ci, [vp, prd, vp, vp, vp]),
@@ -236,6 +238,38 @@ class AccelStructure:
         self.header = hdr
         return self
 
+    def refit(self, vertices: torch.Tensor, faces: torch.Tensor):
+        """Same topology, new vertex positions: rewrite the triangle records and re-fit all node
+        boxes bottom-up in place (rt_bvh_refit) — no sort, no hierarchy emission."""
+        lib = get_module()
+        if self.blob is None:
+            raise RuntimeError("acceleration structure has not been built")
+        if vertices.dtype != torch.float32 or faces.dtype != torch.int32 or not (vertices.is_cuda and faces.is_cuda):
+            raise ValueError("vertices must be float32 and faces int32 CUDA tensors")
+        if faces.shape[0] != self.header["n_tris"]:
+            raise ValueError(f"refit needs the same topology: {faces.shape[0]} faces, BVH was built for {self.header['n_tris']}")
+        vertices = vertices.contiguous()
+        faces = faces.contiguous()
+        dev = self.blob.device
+        wb = C.c_size_t()
+        _check(lib.rt_bvh_refit_sizes(faces.shape[0], C.byref(wb)), "rt_bvh_refit_sizes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(wb.value, 256), dtype=torch.uint8, device=dev)
+            _check(lib.rt_bvh_refit(_ptr(vertices), vertices.shape[0], _ptr(faces), faces.shape[0], _ptr(ws), ws.numel(),
+                                    _ptr(self.blob), self.blob.numel(), _stream(dev)), "rt_bvh_refit")
+            self.header = parse_header(self.blob[:BLOB_HEADER_BYTES].cpu().numpy().tobytes())
+        return self
+
+    def save(self, path: str):
+        """Serialise the used prefix of the blob (header + triangles + nodes)."""
+        torch.save({"format": "triro_b200_bvh8", "abi_version": 1, "blob": self.used().cpu()}, path)
+
+    def load(self, path: str, device="cuda"):
+        d = torch.load(path, map_location="cpu")
+        if d.get("format") != "triro_b200_bvh8" or d.get("abi_version") != 1:
+            raise ValueError(f"{path} is not a BVH blob of this ABI version")
+        return self.adopt(d["blob"].to(device))
+
     def adopt(self, blob: torch.Tensor):
         """Attach to a blob received from elsewhere (NCCL broadcast, torch.load)."""
         hdr = parse_header(blob[:BLOB_HEADER_BYTES].cpu().numpy().tobytes())
@@ -259,9 +293,10 @@ def parse_header(raw: bytes) -> dict:
     tris_off, nodes_off, used = struct.unpack_from("<3Q", raw, 24)
     aabb = struct.unpack_from("<6f", raw, 48)
     bad, overflow = struct.unpack_from("<2I", raw, 72)
+    (parents_off,) = struct.unpack_from("<Q", raw, 80)
     return dict(magic=magic, abi_version=abi, n_tris=n_tris, n_nodes=n_nodes, depth=depth, n_nodes_cap=cap,
                 tris_offset=tris_off, nodes_offset=nodes_off, used_bytes=used, aabb_lo=aabb[:3], aabb_hi=aabb[3:],
-                bad_index_faces=bad, node_overflow=overflow)
+                bad_index_faces=bad, node_overflow=overflow, parents_offset=parents_off)
 
 
 def _blob_of(accel) -> torch.Tensor:

@@ -53,6 +53,19 @@ class RayMeshIntersector:
         self._aabb_host = (self.mesh_aabb[0].tolist(), self.mesh_aabb[1].tolist())
         self.as_wrapper.build_accel_structure(self.mesh_vertices, self.mesh_faces)
 
+    def refit(self, vertices: torch.Tensor):
+        """Extension: move the vertices of the SAME topology and re-fit the BVH in place
+        instead of rebuilding it (`update_raw`, like the reference, always rebuilds).  Results are
+        exact for the deformed mesh; traversal efficiency degrades if the deformation is large."""
+        self.mesh_vertices = vertices.float().contiguous().cuda()
+        self.mesh_aabb = (torch.min(self.mesh_vertices, dim=0)[0], torch.max(self.mesh_vertices, dim=0)[0])
+        self._aabb_host = (self.mesh_aabb[0].tolist(), self.mesh_aabb[1].tolist())
+        self.as_wrapper._inner.refit(self.mesh_vertices, self.mesh_faces)
+
+    def save_bvh(self, path: str):
+        """Extension: write the flat BVH blob to disk."""
+        self.as_wrapper._inner.save(path)
+
     # ------------------------------------------------------------------ queries
     def intersects_any(self, origins: torch.Tensor, directions: torch.Tensor) -> torch.Tensor:
         """Bool[*b] — does each ray hit the mesh (reference :77-82)."""
