@@ -104,9 +104,8 @@ struct U4 { uint32_t x, y, z, w; };
 // ------------------------------------------------------------------ ray set-up
 struct Ray {
     float ox, oy, oz;
-    float dx, dy, dz;
-    // watertight test set-up
-    int kz;
+    // watertight test set-up: kzf = kz | 4 * (d[kz] > 0); the direction itself is not kept (registers)
+    int kzf;
     float Sx, Sy, Sz;
     float okx, oky, okz;           // origin permuted to (kx, ky, kz)
     // slab test set-up
@@ -120,13 +119,11 @@ constexpr uint32_t kByteMagic = 0x47000000u;
 
 RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox; r.oy = oy; r.oz = oz;
-    r.dx = dx; r.dy = dy; r.dz = dz;
     // kz = dimension where |d| is maximal (first maximum in x,y,z order)
     int kz = 0;
     float m = fabsf(dx);
     if (fabsf(dy) > m) { kz = 1; m = fabsf(dy); }
     if (fabsf(dz) > m) { kz = 2; }
-    r.kz = kz;
     const int kx = kz == 2 ? 0 : kz + 1;
     const int ky = kx == 2 ? 0 : kx + 1;
     const float dkx = sel3(kx, dx, dy, dz), dky = sel3(ky, dx, dy, dz), dkz = sel3(kz, dx, dy, dz);
@@ -146,6 +143,7 @@ RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, f
     const uint32_t oct = (sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u);
     r.octinv = 7u - oct;
     r.magic = kByteMagic;
+    r.kzf = kz | (dkz > 0.0f ? 4 : 0);
 }
 
 // ------------------------------------------------------------------ watertight triangle test
@@ -159,9 +157,9 @@ struct TriHit { float t, U, V, W, det; };
 RT_HD bool tri_test(const Ray& r, float v0x, float v0y, float v0z, float v1x, float v1y, float v1z,
                     float v2x, float v2y, float v2z, TriHit& h) {
     float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
-    permute3(r.kz, v0x, v0y, v0z, Akx, Aky, Akz);
-    permute3(r.kz, v1x, v1y, v1z, Bkx, Bky, Bkz);
-    permute3(r.kz, v2x, v2y, v2z, Ckx, Cky, Ckz);
+    permute3(r.kzf & 3, v0x, v0y, v0z, Akx, Aky, Akz);
+    permute3(r.kzf & 3, v1x, v1y, v1z, Bkx, Bky, Bkz);
+    permute3(r.kzf & 3, v2x, v2y, v2z, Ckx, Cky, Ckz);
     Akx = fsub(Akx, r.okx); Aky = fsub(Aky, r.oky); Akz = fsub(Akz, r.okz);
     Bkx = fsub(Bkx, r.okx); Bky = fsub(Bky, r.oky); Bkz = fsub(Bkz, r.okz);
     Ckx = fsub(Ckx, r.okx); Cky = fsub(Cky, r.oky); Ckz = fsub(Ckz, r.okz);
@@ -194,8 +192,7 @@ RT_HD bool tri_test(const Ray& r, float v0x, float v0y, float v0z, float v1x, fl
 // With the fixed cyclic (kx,ky,kz) the sheared edge functions carry the sign of
 // -dot(d, n) * sign(d[kz]) ... so: front <=> (det > 0) == (d[kz] > 0).
 RT_HD bool tri_front(const Ray& r, const TriHit& h) {
-    const float dkz = sel3(r.kz, r.dx, r.dy, r.dz);
-    return (h.det > 0.0f) == (dkz > 0.0f);
+    return (h.det > 0.0f) == ((r.kzf & 4) != 0);
 }
 
 // Closest-hit attributes exactly as the reference computes them (shaders.cu:137-153):
