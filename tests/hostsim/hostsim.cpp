@@ -72,7 +72,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
         hi[0] = fmaxf(hi[0], tb[i].hx); hi[1] = fmaxf(hi[1], tb[i].hy); hi[2] = fmaxf(hi[2], tb[i].hz);
     }
     float inv[3];
-    for (int a = 0; a < 3; ++a) { const float e = hi[a] - lo[a]; inv[a] = e > 0.0f ? 1.0f / e : 0.0f; }
+    morton_scale(lo, hi, inv);
     std::vector<uint64_t> keys((size_t)n);
     std::vector<uint32_t> vals((size_t)n);
     for (int64_t i = 0; i < n; ++i) {

@@ -158,13 +158,10 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ verts,
                                                 const int32_t* __restrict__ faces, int64_t n,
                                                 const BuildState* __restrict__ st, uint64_t* __restrict__ keys,
                                                 uint32_t* __restrict__ vals) {
-    float lo[3], inv[3];
+    float lo[3], hi[3], inv[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        lo[a] = ord2f(st->bounds_lo[a]);
-        const float ext = ord2f(st->bounds_hi[a]) - lo[a];
-        inv[a] = ext > 0.0f ? 1.0f / ext : 0.0f;
-    }
+    for (int a = 0; a < 3; ++a) { lo[a] = ord2f(st->bounds_lo[a]); hi[a] = ord2f(st->bounds_hi[a]); }
+    morton_scale(lo, hi, inv);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float v[9];

@@ -54,6 +54,16 @@ RT_HD uint64_t expand21(uint64_t x) {
     return x;
 }
 
+// One uniform scale for all three axes (the largest scene extent maps to the full 21 bits): the
+// Morton grid cells are cubes, so a flat scene (terrain) is not sliced along its thin axis before it
+// has been subdivided along the long ones; bits that never vary simply create no hierarchy level.
+RT_HD void morton_scale(const float lo[3], const float hi[3], float inv_ext[3]) {
+    float m = 0.0f;
+    for (int a = 0; a < 3; ++a) { const float e = hi[a] - lo[a]; if (e > m) m = e; }
+    const float inv = m > 0.0f ? 1.0f / m : 0.0f;
+    inv_ext[0] = inv_ext[1] = inv_ext[2] = inv;
+}
+
 RT_HD uint64_t morton63(float cx, float cy, float cz, const float lo[3], const float inv_ext[3]) {
     const float scale = 2097152.0f;   // 2^21
     float fx = (cx - lo[0]) * inv_ext[0] * scale;
