@@ -210,14 +210,18 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, 
         const BBox lb = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
         store_box_cg(&box[(n - 1) + k], lb);
         if (n == 1) continue;
-        uint32_t cur = parent[(n - 1) + k];
+        uint32_t me = (uint32_t)((n - 1) + k);
+        uint32_t cur = parent[me];
+        BBox mine = lb;                                    // box of the subtree this thread has completed
         for (;;) {
-            __threadfence();
+            __threadfence();                               // publish box[me] before announcing it
             if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arrival: sibling not ready
-            __threadfence();
-            const BBox u = bbox_union(load_box_cg(&box[left[cur]]), load_box_cg(&box[right[cur]]));
-            store_box_cg(&box[cur], u);
+            const uint32_t l = left[cur];
+            const uint32_t sibling = l == me ? right[cur] : l;
+            mine = bbox_union(mine, load_box_cg(&box[sibling]));   // L1-bypassing load, ordered after the atomic
+            store_box_cg(&box[cur], mine);
             if (cur == 0u) break;
+            me = cur;
             cur = parent[cur];
         }
     }
