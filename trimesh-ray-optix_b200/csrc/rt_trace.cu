@@ -109,7 +109,7 @@ struct VisitorOf {
 
 // A warp re-fills its finished lanes from the global ray counter as soon as fewer than
 // `refill_threshold` lanes are still busy (defaults below; TRIRO_REFILL_THRESHOLD overrides).
-constexpr int kRefillThresholdQueued = 20;
+constexpr int kRefillThresholdQueued = 28;
 constexpr int kRefillThresholdDirect = 8;
 // Postponed triangle tests: every lane owns a queue of pending triangle record indices in shared
 // memory (s_queue[entry][thread], conflict-free).  Node steps only enqueue; a warp runs a triangle
@@ -120,6 +120,7 @@ constexpr int kRefillThresholdDirect = 8;
 constexpr int kQueueCap = 32;
 constexpr int kQueueHigh = kQueueCap - kNodeMaxTris;   // 8: above this a lane may not take a node step
 constexpr int kTriThreshold = 8;
+constexpr int kPoolWords = 13;   // prepared ray: o, S, o permuted, 1/d, packed (kzf | octinv << 8)
 
 struct LaneQueue {
     uint32_t (*q)[kTraceThreads];
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
     using S = typename std::conditional<STATS, Stats, NoStats>::type;
     using Vis = typename VisitorOf<MODE, S>::type;
     __shared__ uint32_t s_queue[QUEUED ? kQueueCap : 1][kTraceThreads];
+    __shared__ float s_pool[QUEUED ? kPoolWords : 1][kTraceThreads];   // prepared rays, column = warp * 32 + slot
     init_mask_luts();
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
     const uint8_t* tris = p.blob + hdr->tris_offset;
@@ -162,20 +164,74 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
     int phase = 0;
     int32_t count_plus = 0;
     trav_init(tv);
+    // per-warp pool of prepared rays (warp-uniform bookkeeping)
+    const int pool_col0 = (int)(threadIdx.x & ~31u);
+    int pool_head = 0, pool_count = 0;
+    int64_t pool_base = 0;
+    // per-warp retire pool (queued closest-hit only; measured slower for coherent batches): finished rays that hit something park
+    // (ray index, triangle record) here; when 32 have gathered the whole warp computes their
+    // attributes at full width (re-fetching the ray, which is cheaper than carrying its set-up)
+    constexpr bool kRetirePool = QUEUED && MODE == kClosest;
+    __shared__ uint32_t s_retire[kRetirePool ? 3 : 1][kTraceThreads];
+    int ret_count = 0;
+    auto flush_retire = [&]() {
+        if (lane < ret_count) {
+            const int col = pool_col0 + lane;
+            const int64_t rr = (int64_t)(((unsigned long long)s_retire[1][col] << 32) | s_retire[0][col]);
+            const uint32_t slot = s_retire[2][col];
+            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, rr);
+            const int64_t os = p.rays.o_stride[3];
+            const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, rr);
+            const int64_t ds = p.rays.d_stride[3];
+            Ray t;
+            ray_setup(t, p.rays.origins[oo], p.rays.origins[oo + os], p.rays.origins[oo + 2 * os], p.rays.directions[dd],
+                      p.rays.directions[dd + ds], p.rays.directions[dd + 2 * ds]);
+            const uint8_t* tp = tris + (size_t)slot * 48u;
+            const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
+            const float v0x = as_float(a.x), v0y = as_float(a.y), v0z = as_float(a.z);
+            const float v1x = as_float(b.x), v1y = as_float(b.y), v1z = as_float(b.z);
+            const float v2x = as_float(c.x), v2y = as_float(c.y), v2z = as_float(c.z);
+            TriHit h;
+            tri_test(t, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h);
+            const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+            p.hit[rr] = 1; p.front[rr] = tri_front(t, h) ? 1 : 0; p.tri[rr] = (int32_t)a.w;
+            p.loc[3 * rr] = at.lx; p.loc[3 * rr + 1] = at.ly; p.loc[3 * rr + 2] = at.lz;
+            p.uv[2 * rr] = at.uv0; p.uv[2 * rr + 1] = at.uv1;
+        }
+        __syncwarp();
+        ret_count = 0;
+    };
 
     for (;;) {
-        // ---- 1. retire finished rays, re-fill free lanes (one atomic per warp)
+        // ---- 1. retire finished rays, re-fill free lanes from the warp's pool of prepared rays
         const bool finished = active && nodes_done && queue.len == 0;
         const unsigned free_lanes = __ballot_sync(0xffffffffu, !active || finished);
         const int busy = 32 - __popc(free_lanes);
-        if (free_lanes != 0u && busy < (exhausted ? 1 : p.refill_threshold)) {
+        if (free_lanes != 0u && busy < ((exhausted && pool_count == 0) ? 1 : p.refill_threshold)) {
+            bool parked = false;
+            if constexpr (kRetirePool) {
+                const bool fin_hit = finished && vis.prim >= 0 && p.hit != nullptr;
+                const unsigned hmask = __ballot_sync(0xffffffffu, fin_hit);
+                if (hmask != 0u) {
+                    const int n_new = __popc(hmask);
+                    if (ret_count + n_new > 32) flush_retire();
+                    if (fin_hit) {
+                        const int col = pool_col0 + ret_count + __popc(hmask & lt_mask);
+                        s_retire[0][col] = (uint32_t)r; s_retire[1][col] = (uint32_t)((unsigned long long)r >> 32);
+                        s_retire[2][col] = vis.slot;
+                        parked = true;
+                    }
+                    __syncwarp();
+                    ret_count += n_new;
+                }
+            }
             if (finished) {
                 if (STATS) { st_nodes += vis.n_nodes(); st_tris += vis.n_tris(); ++st_rays; }
                 if constexpr (MODE == kClosest || MODE == kFirst) {
                     if (STATS) st_hits += vis.prim >= 0;
                     if (MODE == kFirst) {
                         if (p.tri) p.tri[r] = vis.prim;
-                    } else if (p.hit) {
+                    } else if (p.hit && !parked) {
                         if (vis.prim >= 0) {
                             const uint8_t* tp = tris + (size_t)vis.slot * 48u;
                             const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
@@ -231,29 +287,60 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                     }
                 }
             }
-            const unsigned idle = __ballot_sync(0xffffffffu, !active);
-            if (idle != 0u && !exhausted) {
-                const int n_idle = __popc(idle);
-                const int leader = __ffs((int)idle) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if ((int64_t)base + n_idle >= nray) exhausted = true;
-                if (!active) {
-                    r = (int64_t)base + __popc(idle & lt_mask);
-                    if (r < nray) {
-                        const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
-                        const int64_t os = p.rays.o_stride[3];
-                        const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
-                        float dx, dy, dz;
-                        if (MODE == kContains) {
-                            dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
-                        } else {
-                            const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
-                            const int64_t ds = p.rays.d_stride[3];
-                            dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+            if constexpr (QUEUED) {
+                // incoherent batches re-fill early and often: rays are prepared 32 at a time by the whole
+                // warp (coalesced fetch, full-width set-up) into a shared-memory pool; a lane that frees
+                // up only copies a prepared ray
+                for (;;) {
+                    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+                    if (idle == 0u) break;
+                    if (pool_count == 0) {
+                        if (exhausted) break;
+                        // prepare the next 32 rays with the whole warp: coalesced fetch, full-width set-up
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(p.ray_counter, 32ull);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        int64_t n = nray - (int64_t)base;
+                        if (n <= 32) exhausted = true;
+                        if (n <= 0) break;
+                        if (n > 32) n = 32;
+                        if (lane < n) {
+                            const int64_t rr = (int64_t)base + lane;
+                            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, rr);
+                            const int64_t os = p.rays.o_stride[3];
+                            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
+                            float dx, dy, dz;
+                            if (MODE == kContains) {
+                                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+                            } else {
+                                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, rr);
+                                const int64_t ds = p.rays.d_stride[3];
+                                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+                            }
+                            Ray t;
+                            ray_setup(t, ox, oy, oz, dx, dy, dz);
+                            const int col = pool_col0 + lane;
+                            s_pool[0][col] = t.ox; s_pool[1][col] = t.oy; s_pool[2][col] = t.oz;
+                            s_pool[3][col] = t.Sx; s_pool[4][col] = t.Sy; s_pool[5][col] = t.Sz;
+                            s_pool[6][col] = t.okx; s_pool[7][col] = t.oky; s_pool[8][col] = t.okz;
+                            s_pool[9][col] = t.idx; s_pool[10][col] = t.idy; s_pool[11][col] = t.idz;
+                            s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8));
                         }
-                        ray_setup(ray, ox, oy, oz, dx, dy, dz);
+                        __syncwarp();
+                        pool_base = (int64_t)base; pool_head = 0; pool_count = (int)n;
+                    }
+                    const int n_idle = __popc(idle);
+                    const int take = n_idle < pool_count ? n_idle : pool_count;
+                    const int my = __popc(idle & lt_mask);
+                    if (!active && my < take) {
+                        const int col = pool_col0 + pool_head + my;
+                        r = pool_base + pool_head + my;
+                        ray.ox = s_pool[0][col]; ray.oy = s_pool[1][col]; ray.oz = s_pool[2][col];
+                        ray.Sx = s_pool[3][col]; ray.Sy = s_pool[4][col]; ray.Sz = s_pool[5][col];
+                        ray.okx = s_pool[6][col]; ray.oky = s_pool[7][col]; ray.okz = s_pool[8][col];
+                        ray.idx = s_pool[9][col]; ray.idy = s_pool[10][col]; ray.idz = s_pool[11][col];
+                        const int packed = __float_as_int(s_pool[12][col]);
+                        ray.kzf = packed & 0xff; ray.octinv = (uint32_t)packed >> 8;
                         ray.magic = p.byte_magic;
                         trav_init(tv);
                         vis = Vis(p.tmax);
@@ -263,6 +350,45 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                         phase = 0;
                         nodes_done = false;
                         active = true;
+                    }
+                    __syncwarp();
+                    pool_head += take; pool_count -= take;
+                }
+            } else {
+                // coherent batches re-fill late (most lanes at once): fetch and set up in place
+                const unsigned idle = __ballot_sync(0xffffffffu, !active);
+                if (idle != 0u && !exhausted) {
+                    const int n_idle = __popc(idle);
+                    const int leader = __ffs((int)idle) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if ((int64_t)base + n_idle >= nray) exhausted = true;
+                    if (!active) {
+                        r = (int64_t)base + __popc(idle & lt_mask);
+                        if (r < nray) {
+                            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
+                            const int64_t os = p.rays.o_stride[3];
+                            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
+                            float dx, dy, dz;
+                            if (MODE == kContains) {
+                                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+                            } else {
+                                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
+                                const int64_t ds = p.rays.d_stride[3];
+                                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+                            }
+                            ray_setup(ray, ox, oy, oz, dx, dy, dz);
+                            ray.magic = p.byte_magic;
+                            trav_init(tv);
+                            vis = Vis(p.tmax);
+                            if constexpr (MODE == kAllHits) {
+                                vis.max_hits = p.max_hits; vis.out = p.staging + (size_t)r * p.max_hits; vis.tris = tris;
+                            }
+                            phase = 0;
+                            nodes_done = false;
+                            active = true;
+                        }
                     }
                 }
             }
@@ -290,6 +416,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
             }
         }
     }
+    if constexpr (kRetirePool) flush_retire();
     if (MODE == kContains) {
         if (__any_sync(0xffffffffu, any_inside) && lane == 0) atomicOr(&p.flags[0], 1);
         if (__any_sync(0xffffffffu, any_broken) && lane == 0) atomicOr(&p.flags[1], 1);
