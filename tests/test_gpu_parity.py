@@ -577,3 +577,43 @@ def test_numpy_adapter_follows_trimesh_ray_conventions(cuda_device):
     t2, r2 = ray.intersects_id(o64, d64, multiple_hits=False)
     assert np.array_equal(t2, index_tri) and np.array_equal(r2, index_ray)
     assert ray.contains_points(np.array([[0, 0, 0.999], [0, 0, 1.5]])).tolist() == [True, False]
+
+
+# ---------------------------------------------------------------- property test: arbitrary strided views
+def test_random_strided_views_equal_their_contiguous_copies(cuda_device):
+    """the kernels read rays through shape[4]/stride[4] exactly like the reference's getRay
+    (shaders.cu:27-63); any view must give the answer of its contiguous copy."""
+    from hypothesis import given, settings, strategies as st
+
+    v, f = synth.icosphere(2)
+    r = make(v, f)
+    base_o = (torch.rand((6, 5, 4, 7, 3), generator=torch.Generator().manual_seed(1)) * 4 - 2).to(cuda_device)
+    base_d = torch.randn((6, 5, 4, 7, 3), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 3), st.permutations([0, 1, 2]), st.integers(0, 3), st.integers(1, 2), st.booleans(), st.integers(0, 2),
+           st.booleans())
+    def run(ndim, perm, start, step, bcast_o, chan_off, neg):
+        # carve a [*b, 3] view out of the 5-D base: drop leading dims, permute batch dims, slice with a step,
+        # take 3 of the 7 channels with stride 2 (non-unit last-dim stride)
+        def view(t):
+            x = t[0] if ndim < 3 else t                       # [5,4,7,3] or [6,5,4,7,3]
+            x = x[..., chan_off::2, 0][..., :3] if not neg else x[..., chan_off:chan_off + 3, 1]   # last dim 3, stride 6 or 3
+            if ndim == 1:
+                x = x[0, start::step]                         # [k,3]
+            elif ndim == 2:
+                x = x[:, start::step].transpose(0, 1)          # [k,5,3] transposed
+            else:
+                x = x.permute(*perm, 3)[:, start::step]
+            return x
+        o, d = view(base_o), view(base_d)
+        if bcast_o:
+            o = torch.tensor([0.3, -0.2, 2.0], device=cuda_device).broadcast_to(d.shape)
+        assert o.shape == d.shape and o.shape[-1] == 3 and 1 <= o.dim() - 1 <= 3
+        a = r.intersects_closest(o, d)
+        b = r.intersects_closest(o.contiguous(), d.contiguous())
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and torch.equal(x, y)
+        assert torch.equal(r.intersects_count(o, d), r.intersects_count(o.contiguous(), d.contiguous()))
+
+    run()
