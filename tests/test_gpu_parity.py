@@ -617,3 +617,22 @@ def test_random_strided_views_equal_their_contiguous_copies(cuda_device):
         assert torch.equal(r.intersects_count(o, d), r.intersects_count(o.contiguous(), d.contiguous()))
 
     run()
+
+
+def test_more_than_2_to_31_rays_use_64_bit_indexing(cuda_device):
+    """The reference's `int float_idx = idx * 3` overflows at 715 M rays (shaders.cu:37) and OptiX launches are
+    limited to 2^30; here ray indices are 64-bit.  2.19 G rays as stride-0 broadcast views (no input memory),
+    any-hit output 2.19 GB; the result must be the 27 000-ray answer tiled."""
+    v, f = synth.icosphere(2)
+    r = make(v, f)
+    k = 27_000
+    o1, d1 = synth.random_rays(k, seed=77, device=cuda_device, box=True)
+    o1 = o1 * 2
+    small = r.intersects_any(o1, d1)
+    o = o1.unsqueeze(0).unsqueeze(0).expand(3, k, k, 3)          # strides (0, 0, 3, 1)
+    d = d1.unsqueeze(0).unsqueeze(0).expand(3, k, k, 3)
+    assert o.numel() // 3 > 2 ** 31
+    big = r.intersects_any(o, d)
+    assert big.shape == (3, k, k)
+    assert torch.equal(big[0, 0], small) and torch.equal(big[2, k - 1], small) and torch.equal(big[1, 12345], small)
+    assert int(big.sum()) == 3 * k * int(small.sum())
