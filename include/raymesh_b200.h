@@ -125,6 +125,17 @@ int rt_trace_first(const void* blob, const rt_ray_desc* rays, int32_t* tri_idx, 
  * hit u8, front u8, tri i32 (-1 on miss), loc f32x3 (0 on miss), uv f32x2 = (w0, w1) (0 on miss). */
 int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8_t* hit, uint8_t* front,
                      int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
+/* Fused ray generation + closest hit: the pinhole rays of the reference's benchmark
+ * (gen_rays, test/performance_test.py:10-20: d = normalize(x-(w-1)/2, y-(h-1)/2, -f) @ cam_mat^T, all rays
+ * from `origin`) are generated in registers, so no ray tensor is read.  Outputs are [height, width] dense. */
+typedef struct rt_pinhole {
+    int64_t width, height;
+    float focal;
+    float cam_mat[9];   /* row-major 3x3 */
+    float origin[3];
+} rt_pinhole;
+int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, uint8_t* hit, uint8_t* front,
+                             int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
 /* replaces intersectsCount (ray.cpp:291-322; shaders.cu:176-194): exact number of triangles hit. */
 int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream);
 

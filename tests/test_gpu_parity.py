@@ -636,3 +636,36 @@ def test_more_than_2_to_31_rays_use_64_bit_indexing(cuda_device):
     assert big.shape == (3, k, k)
     assert torch.equal(big[0, 0], small) and torch.equal(big[2, k - 1], small) and torch.equal(big[1, 12345], small)
     assert int(big.sum()) == 3 * k * int(small.sum())
+
+
+def test_fused_pinhole_generation_matches_explicit_rays(cuda_device):
+    """rays of the reference benchmark's camera (test/performance_test.py:10-36, its cam_mat and
+    the 640x360 / f = 444 set-up) generated inside the kernel vs the explicit gen_rays tensors.  Ray directions agree to
+    rounding (the kernel and torch associate the 3x3 product differently), so masks / indices must agree except on a
+    handful of edge-grazing pixels and locations to 1e-5."""
+    cam_mat = torch.tensor([[5.6272650e-01, 2.7091104e-01, 7.8099048e-01], [8.2602328e-01, -1.4769979e-01, -5.4393965e-01],
+                            [3.2007132e-02, -9.5120555e-01, 3.0689341e-01]])
+    w, h, f = 640, 360, float(int(640 * 25 / 36))
+    v, fa = synth.icosphere(5)
+    # put the sphere in front of that camera: camera looks along -z of cam space = -cam_mat[:, 2]
+    origin = (cam_mat[:, 2] * 3.0)
+    r = make(v, fa)
+    dirs = synth.gen_rays(cam_mat, w, h, f, device=cuda_device)
+    o = origin.to(cuda_device).broadcast_to(dirs.shape)
+    exp = r.intersects_closest(o, dirs)
+    got = r.intersects_closest_pinhole(cam_mat, origin, w, h, f)
+    assert got[0].shape == (h, w) and got[3].shape == (h, w, 3)
+    assert 0.2 < float(exp[0].float().mean()) < 0.9
+    differ = (got[0] != exp[0]) | (got[2] != exp[2])
+    assert int(differ.sum()) <= 1e-4 * w * h, int(differ.sum())
+    same = ~differ & exp[0]
+    # 1-ulp differences in the directions are amplified at silhouette pixels (grazing incidence)
+    assert float((got[3][same] - exp[3][same]).abs().max()) < 5e-5
+    assert float((got[3][same] - exp[3][same]).abs().mean()) < 1e-6
+    assert torch.equal(got[1][same], exp[1][same])
+    # compaction variant and the demo's normal interpolation post-op (test/test.py:35-42)
+    c = r.intersects_closest_pinhole(cam_mat, origin, w, h, f, stream_compaction=True)
+    assert torch.equal(c[0], got[0]) and torch.equal(c[3], got[2][got[0]])
+    normals = torch.from_numpy(v).to(cuda_device)                      # unit sphere: vertex normal = position
+    n = r.interpolate(normals, c[3], c[5])
+    assert float((n - c[4]).abs().max()) < 1e-5                        # interpolated position attribute == hit location

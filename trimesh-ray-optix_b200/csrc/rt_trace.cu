@@ -47,6 +47,10 @@ struct TraceParams {
     int32_t* flags;
     // instrumentation
     unsigned long long* counters;
+    // fused pinhole ray generation (o_mode == kPinhole): r -> pixel (x = r % w, y = r / w)
+    long long cam_w;
+    float cam_half_w, cam_half_h, cam_f;
+    float cam_mat[9], cam_origin[3];
 };
 
 struct LocalStack {
@@ -55,7 +59,7 @@ struct LocalStack {
     __device__ __forceinline__ void pop(int sp, uint32_t& x, uint32_t& y) { const uint2 v = e[sp]; x = v.x; y = v.y; }
 };
 
-enum FetchMode { kGeneral = 0, kPacked = 1, kConstant = 2, kGeneral32 = 3 };
+enum FetchMode { kGeneral = 0, kPacked = 1, kConstant = 2, kGeneral32 = 3, kPinhole = 4 };
 
 __device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int64_t stride[4], int mode, int64_t r) {
     if (mode == kPacked) return 3 * r;
@@ -71,6 +75,35 @@ __device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int6
     const int64_t i1 = q % shape[1];
     const int64_t i0 = q / shape[1];
     return i0 * stride[0] + i1 * stride[1] + i2 * stride[2];
+}
+
+// Origin and direction of ray r: strided fetch (reference getRay, shaders.cu:35-63), the fixed direction
+// of contains_points, or a pinhole camera ray generated in registers (reference gen_rays,
+// test/performance_test.py:10-20: d = normalize(x - (w-1)/2, y - (h-1)/2, -f) @ cam_mat^T).
+template <int MODE>
+__device__ __forceinline__ void load_ray(const TraceParams& p, int64_t r, float& ox, float& oy, float& oz, float& dx,
+                                         float& dy, float& dz) {
+    if (p.o_mode == kPinhole) {
+        const long long y = r / p.cam_w, x = r - y * p.cam_w;
+        const float px = (float)x - p.cam_half_w, py = (float)y - p.cam_half_h, pz = -p.cam_f;
+        const float n = sqrtf(px * px + py * py + pz * pz);
+        const float cx = px / n, cy = py / n, cz = pz / n;
+        dx = cx * p.cam_mat[0] + cy * p.cam_mat[1] + cz * p.cam_mat[2];
+        dy = cx * p.cam_mat[3] + cy * p.cam_mat[4] + cz * p.cam_mat[5];
+        dz = cx * p.cam_mat[6] + cy * p.cam_mat[7] + cz * p.cam_mat[8];
+        ox = p.cam_origin[0]; oy = p.cam_origin[1]; oz = p.cam_origin[2];
+        return;
+    }
+    const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
+    const int64_t os = p.rays.o_stride[3];
+    ox = p.rays.origins[oo]; oy = p.rays.origins[oo + os]; oz = p.rays.origins[oo + 2 * os];
+    if (MODE == kContains) {
+        dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
+    } else {
+        const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
+        const int64_t ds = p.rays.d_stride[3];
+        dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
+    }
 }
 
 // records up to max_hits (tri, loc) per ray in traversal order, like the reference's
@@ -179,13 +212,10 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
             const int col = pool_col0 + lane;
             const int64_t rr = (int64_t)(((unsigned long long)s_retire[1][col] << 32) | s_retire[0][col]);
             const uint32_t slot = s_retire[2][col];
-            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, rr);
-            const int64_t os = p.rays.o_stride[3];
-            const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, rr);
-            const int64_t ds = p.rays.d_stride[3];
+            float ox, oy, oz, dx, dy, dz;
+            load_ray<MODE>(p, rr, ox, oy, oz, dx, dy, dz);
             Ray t;
-            ray_setup(t, p.rays.origins[oo], p.rays.origins[oo + os], p.rays.origins[oo + 2 * os], p.rays.directions[dd],
-                      p.rays.directions[dd + ds], p.rays.directions[dd + 2 * ds]);
+            ray_setup(t, ox, oy, oz, dx, dy, dz);
             const uint8_t* tp = tris + (size_t)slot * 48u;
             const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
             const float v0x = as_float(a.x), v0y = as_float(a.y), v0z = as_float(a.z);
@@ -305,18 +335,8 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                         if (n <= 0) break;
                         if (n > 32) n = 32;
                         if (lane < n) {
-                            const int64_t rr = (int64_t)base + lane;
-                            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, rr);
-                            const int64_t os = p.rays.o_stride[3];
-                            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
-                            float dx, dy, dz;
-                            if (MODE == kContains) {
-                                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
-                            } else {
-                                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, rr);
-                                const int64_t ds = p.rays.d_stride[3];
-                                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
-                            }
+                            float ox, oy, oz, dx, dy, dz;
+                            load_ray<MODE>(p, (int64_t)base + lane, ox, oy, oz, dx, dy, dz);
                             Ray t;
                             ray_setup(t, ox, oy, oz, dx, dy, dz);
                             const int col = pool_col0 + lane;
@@ -367,17 +387,8 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                     if (!active) {
                         r = (int64_t)base + __popc(idle & lt_mask);
                         if (r < nray) {
-                            const int64_t oo = ray_offset(p.rays.shape, p.rays.o_stride, p.o_mode, r);
-                            const int64_t os = p.rays.o_stride[3];
-                            const float ox = p.rays.origins[oo], oy = p.rays.origins[oo + os], oz = p.rays.origins[oo + 2 * os];
-                            float dx, dy, dz;
-                            if (MODE == kContains) {
-                                dx = p.dir[0]; dy = p.dir[1]; dz = p.dir[2];
-                            } else {
-                                const int64_t dd = ray_offset(p.rays.shape, p.rays.d_stride, p.d_mode, r);
-                                const int64_t ds = p.rays.d_stride[3];
-                                dx = p.rays.directions[dd]; dy = p.rays.directions[dd + ds]; dz = p.rays.directions[dd + 2 * ds];
-                            }
+                            float ox, oy, oz, dx, dy, dz;
+                            load_ray<MODE>(p, r, ox, oy, oz, dx, dy, dz);
                             ray_setup(ray, ox, oy, oz, dx, dy, dz);
                             ray.magic = p.byte_magic;
                             trav_init(tv);
@@ -485,15 +496,20 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
                   cudaStream_t stream) {
     RT_REQUIRE(blob != nullptr && ((uintptr_t)blob & 15) == 0, RT_ERR_INVALID, "%s: blob null or not 16-byte aligned", fn);
     RT_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 7) == 0, RT_ERR_INVALID, "%s: scratch null or misaligned", fn);
-    const int rc = check_rays(fn, rays, MODE != kContains);
-    if (rc != RT_OK) return rc;
+    const bool pinhole = p.o_mode == kPinhole;     // preset by rt_trace_closest_pinhole: rays are generated, not fetched
+    if (!pinhole) {
+        const int rc = check_rays(fn, rays, MODE != kContains);
+        if (rc != RT_OK) return rc;
+    }
     if (rays->nray == 0) return RT_OK;
     DeviceInfo dev;
     RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "%s: no CUDA device", fn);
     p.blob = reinterpret_cast<const uint8_t*>(blob);
     p.rays = *rays;
-    p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
-    p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
+    if (!pinhole) {
+        p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
+        p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
+    }
     p.tmax = RT_TMAX_DEFAULT;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
@@ -502,7 +518,7 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     // rays, reference README.md:38 and test/performance_test.py:36-41) are coherent and mostly
     // short: test triangles inside the node step and re-fill lanes late.  Anything else is treated
     // as incoherent: postponed triangle tests, early re-fill.  TRIRO_TRI_MODE=0/1 overrides.
-    const int queued_default = (MODE != kContains && p.o_mode == kConstant) ? 0 : 1;
+    const int queued_default = (MODE != kContains && (p.o_mode == kConstant || pinhole)) ? 0 : 1;
     const bool queued = env_int("TRIRO_TRI_MODE", queued_default, 0, 1) != 0;
     p.refill_threshold = env_int("TRIRO_REFILL_THRESHOLD", queued ? kRefillThresholdQueued : kRefillThresholdDirect, 1, 32);
     p.tri_threshold = env_int("TRIRO_TRI_THRESHOLD", kTriThreshold, 1, 32);
@@ -549,6 +565,24 @@ extern "C" int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8
     TraceParams p = {};
     p.hit = hit; p.front = front; p.tri = tri_idx; p.loc = loc; p.uv = uv;
     return launch<kClosest, false>("rt_trace_closest", p, blob, rays, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, uint8_t* hit, uint8_t* front,
+                                        int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream) {
+    RT_REQUIRE(cam != nullptr && cam->width > 0 && cam->height > 0 && cam->focal > 0.0f, RT_ERR_INVALID,
+               "rt_trace_closest_pinhole: bad camera");
+    RT_REQUIRE(hit && front && tri_idx && loc && uv, RT_ERR_INVALID, "rt_trace_closest_pinhole: null output");
+    TraceParams p = {};
+    p.hit = hit; p.front = front; p.tri = tri_idx; p.loc = loc; p.uv = uv;
+    p.o_mode = kPinhole; p.d_mode = kPinhole;
+    p.cam_w = cam->width;
+    p.cam_half_w = (float)(cam->width - 1) / 2.0f; p.cam_half_h = (float)(cam->height - 1) / 2.0f; p.cam_f = cam->focal;
+    for (int i = 0; i < 9; ++i) p.cam_mat[i] = cam->cam_mat[i];
+    for (int i = 0; i < 3; ++i) p.cam_origin[i] = cam->origin[i];
+    rt_ray_desc rd = {};
+    rd.nray = cam->width * cam->height;
+    rd.shape[0] = 1; rd.shape[1] = cam->height; rd.shape[2] = cam->width; rd.shape[3] = 3;
+    return launch<kClosest, false>("rt_trace_closest_pinhole", p, blob, &rd, scratch, (cudaStream_t)stream);
 }
 
 extern "C" int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream) {

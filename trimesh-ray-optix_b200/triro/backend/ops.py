@@ -44,6 +44,13 @@ class RayDesc(C.Structure):
     ]
 
 
+class Pinhole(C.Structure):
+    """rt_pinhole — camera of the fused ray-generation entry point."""
+
+    _fields_ = [("width", C.c_int64), ("height", C.c_int64), ("focal", C.c_float), ("cam_mat", C.c_float * 9),
+                ("origin", C.c_float * 3)]
+
+
 def _declare(lib):
     vp, i64, sz, ci = C.c_void_p, C.c_int64, C.c_size_t, C.c_int
     psz = C.POINTER(C.c_size_t)
@@ -62,6 +69,7 @@ def _declare(lib):
         "rt_trace_first": (ci, [vp, prd, vp, vp, vp]),
         "rt_trace_closest": (ci, [vp, prd, vp, vp, vp, vp, vp, vp, vp]),
         "rt_trace_count": (ci, [vp, prd, vp, vp, vp]),
+        "rt_trace_closest_pinhole": (ci, [vp, C.POINTER(Pinhole), vp, vp, vp, vp, vp, vp, vp]),
         "rt_compact_sizes": (ci, [i64, psz]),
         "rt_compact_scan": (ci, [vp, i64, vp, sz, vp, vp]),
         "rt_compact_scatter": (ci, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -348,6 +356,34 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
         uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
         _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc),
                                              _ptr(uv), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest")
+    return hit, front, tri, loc, uv
+
+
+def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int, height: int, focal: float):
+    """Closest hit of the pinhole camera rays of the reference's benchmark (gen_rays,
+    test/performance_test.py:10-20) generated inside the kernel: no ray tensors are built or read.
+    Returns (hit[h,w], front[h,w], tri[h,w], loc[h,w,3], uv[h,w,2])."""
+    blob = _blob_of(accel_structure)
+    dev = blob.device
+    cam = Pinhole()
+    cam.width, cam.height, cam.focal = int(width), int(height), float(focal)
+    m = [float(x) for x in torch.as_tensor(cam_mat).reshape(-1).tolist()]
+    o = [float(x) for x in torch.as_tensor(cam_origin).reshape(-1).tolist()]
+    if len(m) != 9 or len(o) != 3:
+        raise ValueError("cam_mat must be 3x3 and cam_origin a 3-vector")
+    for i in range(9):
+        cam.cam_mat[i] = m[i]
+    for i in range(3):
+        cam.origin[i] = o[i]
+    batch = (int(height), int(width))
+    with torch.cuda.device(dev):
+        hit = torch.empty(batch, dtype=torch.bool, device=dev)
+        front = torch.empty(batch, dtype=torch.bool, device=dev)
+        tri = torch.empty(batch, dtype=torch.int32, device=dev)
+        loc = torch.empty((*batch, 3), dtype=torch.float32, device=dev)
+        uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
+        _check(get_module().rt_trace_closest_pinhole(_ptr(blob), C.byref(cam), _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc),
+                                                     _ptr(uv), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest_pinhole")
     return hit, front, tri, loc, uv
 
 

@@ -88,6 +88,24 @@ class RayMeshIntersector:
             return hit, front_c, ray_idx, tri_c, loc_c, uv_c
         return hit, front, tri_idx, loc, uv
 
+    def intersects_closest_pinhole(self, cam_mat, cam_origin, width: int, height: int, focal: float,
+                                   stream_compaction: bool = False):
+        """Extension: `intersects_closest` for the pinhole camera of the reference's benchmark
+        (`gen_rays`, test/performance_test.py:10-20) with the rays generated inside the kernel.  Same tuples as
+        `intersects_closest`, batch shape [height, width]."""
+        hit, front, tri_idx, loc, uv = hops.intersects_closest_pinhole(self.as_wrapper, cam_mat, cam_origin, width, height, focal)
+        if stream_compaction:
+            front_c, ray_idx, tri_c, loc_c, uv_c = hops.compact_closest(hit, front, tri_idx, loc, uv)
+            return hit, front_c, ray_idx, tri_c, loc_c, uv_c
+        return hit, front, tri_idx, loc, uv
+
+    def interpolate(self, vertex_attribute: torch.Tensor, tri_idx: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
+        """Extension: barycentric interpolation of a per-vertex attribute at hit points, the post-op of
+        the reference demo (test/test.py:35-42): uv0 * a[f0] + uv1 * a[f1] + (1 - uv0 - uv1) * a[f2]."""
+        a = vertex_attribute.to(self.mesh_vertices.device)[self.mesh_faces[tri_idx.long()].long()]
+        w0, w1 = uv[..., :1], uv[..., 1:]
+        return w0 * a[..., 0, :] + w1 * a[..., 1, :] + (1 - w0 - w1) * a[..., 2, :]
+
     def intersects_location(self, origins: torch.Tensor, directions: torch.Tensor
                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(loc[h,3], ray_idx[h], tri_idx[h]) for every hit, at most 8 per ray (reference :157-164)."""

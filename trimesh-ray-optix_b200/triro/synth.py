@@ -19,6 +19,7 @@ __all__ = [
     "cube",
     "readme_rays",
     "pinhole_rays",
+    "gen_rays",
     "random_rays",
 ]
 
@@ -119,6 +120,19 @@ def pinhole_rays(w: int = 3840, h: int = 2160, device="cpu", origin=(0.0, 0.0, 3
     d = d / torch.norm(d, dim=-1, keepdim=True)
     o = torch.tensor(origin, dtype=torch.float32, device=device).broadcast_to(d.shape)
     return o, d.contiguous()
+
+
+def gen_rays(cam_mat, w: int, h: int, f: float, device="cpu"):
+    """The reference's gen_rays (test/performance_test.py:10-20) verbatim in behaviour: [h, w, 3] directions."""
+    import torch
+
+    y, x = torch.meshgrid([torch.linspace(0, h - 1, h), torch.linspace(0, w - 1, w)], indexing="ij")
+    x = x - (w - 1) / 2
+    y = y - (h - 1) / 2
+    z = -torch.ones_like(x) * f
+    dirs = torch.stack([x, y, z], dim=-1).to(device)
+    dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+    return dirs @ torch.transpose(torch.as_tensor(cam_mat, dtype=torch.float32, device=device), 0, 1)
 
 
 def random_rays(n: int, seed: int = 1234, device="cpu", zlo: float = 0.3, zhi: float = 0.5, box: bool = False):
