@@ -118,6 +118,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
         begin = end;
         end = node_count < lay.node_cap ? node_count : lay.node_cap;
     }
+    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, vals.data(), verts, nv, faces);
     h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
     for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
     h.node_overflow = node_count > lay.node_cap ? 1u : 0u;

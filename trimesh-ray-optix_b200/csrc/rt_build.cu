@@ -142,7 +142,22 @@ __global__ void __launch_bounds__(256) k_scene_bounds(const float* __restrict__ 
         }
         bad += __shfl_xor_sync(0xffffffffu, bad, o);
     }
+    // block-level reduction first: one set of atomics per CTA instead of per warp
+    __shared__ float s_lo[8][3], s_hi[8][3];
+    __shared__ uint32_t s_bad[8];
+    const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+        s_bad[warp] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], s_lo[w][a]); hi[a] = fmaxf(hi[a], s_hi[w][a]); }
+            bad += s_bad[w];
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (lo[a] <= hi[a]) {
@@ -245,6 +260,14 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, CollapseOut o, c
         end = new_end;
     }
     if (gtid == 0) st->depth = depth;
+}
+
+__global__ void __launch_bounds__(256) k_fill_tris(const float* __restrict__ verts, int64_t nv,
+                                                   const int32_t* __restrict__ faces, int64_t n,
+                                                   const uint32_t* __restrict__ sorted_prim, uint8_t* tris) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        fill_tri_record(tris, (uint32_t)i, sorted_prim, verts, nv, faces);
 }
 
 __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n, BlobLayout lay) {
@@ -358,6 +381,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         BuildState* stp = w.state;
         void* args[] = {&t, &o, (void*)&vertices, (void*)&n_verts, (void*)&faces, &stp};
         RT_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(cgrid), dim3(128), args, 0, stream));
+        k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.vals, blob8 + lay.tris_offset);
     }
     k_finalize<<<1, 32, 0, stream>>>(hdr, w.state, n, lay);
     RT_CUDA_TRY(cudaGetLastError());

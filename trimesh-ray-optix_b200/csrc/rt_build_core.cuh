@@ -260,6 +260,13 @@ RT_HD void write_tri_record(uint8_t* tris, uint32_t slot, uint32_t prim, const f
     *reinterpret_cast<TriRecord*>(tris + (size_t)slot * 48u) = tr;
 }
 
+// second half of the collapse: record `slot` holds a sorted position; resolve it to the face and write the record
+RT_HD void fill_tri_record(uint8_t* tris, uint32_t slot, const uint32_t* __restrict__ sorted_prim,
+                           const float* __restrict__ verts, int64_t n_verts, const int32_t* __restrict__ faces) {
+    const uint32_t pos = *reinterpret_cast<const uint32_t*>(tris + (size_t)slot * 48u + 12);
+    write_tri_record(tris, slot, sorted_prim[pos], verts, n_verts, faces);
+}
+
 // Bottom-up update of one wide node after its children are final (refit): recomputes the slot
 // boxes (leaf slots from their triangle records, inner slots from child_box[]), re-quantises and
 // returns the node's own box.  Topology fields are untouched.
@@ -391,8 +398,11 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             trimask |= unary << (3 * s);
             const uint32_t f0 = bt_first(t, ref[i]);
+            // only the SORTED POSITION of each triangle is recorded here (in the record's prim field); the
+            // dependent gathers position -> face -> vertices run afterwards in a fully parallel pass
+            // (fill_tri_record), not serially inside this node's thread
             for (uint32_t j = 0; j < cnt; ++j)
-                write_tri_record(o.tris, tri_base + toff + j, t.sorted_prim[f0 + j], verts, n_verts, faces);
+                *reinterpret_cast<uint32_t*>(o.tris + (size_t)(tri_base + toff + j) * 48u + 12) = f0 + j;
             toff += cnt;
         }
     }
