@@ -230,11 +230,12 @@ RT_HD void quantise_slots(const BBox& nb, const BBox slot_box[8], uint32_t prese
             const float cl = a == 0 ? slot_box[s].lx : (a == 1 ? slot_box[s].ly : slot_box[s].lz);
             const float ch = a == 0 ? slot_box[s].hx : (a == 1 ? slot_box[s].hy : slot_box[s].hz);
             const double sc = (double)exp2_biased(e[a]);
-            double fl = floor(((double)cl - (double)p[a]) / sc);
+            const double isc = (double)exp2_biased(254u - e[a]);   // exact 1/sc (power of two): no double division
+            double fl = floor(((double)cl - (double)p[a]) * isc);
             if (!(fl >= 0.0)) fl = 0.0;
             if (fl > 255.0) fl = 255.0;
             while (fl > 0.0 && (double)p[a] + fl * sc > (double)cl) fl -= 1.0;
-            double fh = ceil(((double)ch - (double)p[a]) / sc);
+            double fh = ceil(((double)ch - (double)p[a]) * isc);
             if (!(fh >= 0.0)) fh = 0.0;
             if (fh > 255.0) fh = 255.0;
             while (fh < 255.0 && (double)p[a] + fh * sc < (double)ch) fh += 1.0;
