@@ -99,6 +99,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
         for (;;) {
             if (flags[cur]++ == 0) break;
             box[cur] = bbox_union(box[left[cur]], box[right[cur]]);
+            memcpy(&box[cur].pad0, &left[cur], 4); memcpy(&box[cur].pad1, &right[cur], 4);   // child refs ride in the pads
             if (cur == 0) break;
             cur = parent[cur];
         }

@@ -207,9 +207,10 @@ __device__ __forceinline__ BBox load_box_cg(const BBox* p) {
     BBox r; r.lx = a.x; r.ly = a.y; r.lz = a.z; r.pad0 = 0.f; r.hx = b.x; r.hy = b.y; r.hz = b.z; r.pad1 = 0.f;
     return r;
 }
-__device__ __forceinline__ void store_box_cg(BBox* p, const BBox& b) {
-    __stcg(reinterpret_cast<float4*>(p), make_float4(b.lx, b.ly, b.lz, 0.f));
-    __stcg(reinterpret_cast<float4*>(p) + 1, make_float4(b.hx, b.hy, b.hz, 0.f));
+__device__ __forceinline__ void store_box_cg(BBox* p, const BBox& b, uint32_t left = 0u, uint32_t right = 0u) {
+    // the pad words of an inner node's record carry its child references (used by the collapse)
+    __stcg(reinterpret_cast<float4*>(p), make_float4(b.lx, b.ly, b.lz, __uint_as_float(left)));
+    __stcg(reinterpret_cast<float4*>(p) + 1, make_float4(b.hx, b.hy, b.hz, __uint_as_float(right)));
 }
 
 __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, int64_t nv,
@@ -231,10 +232,10 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, 
         for (;;) {
             __threadfence();                               // publish box[me] before announcing it
             if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arrival: sibling not ready
-            const uint32_t l = left[cur];
-            const uint32_t sibling = l == me ? right[cur] : l;
+            const uint32_t l = left[cur], rr = right[cur];
+            const uint32_t sibling = l == me ? rr : l;
             mine = bbox_union(mine, load_box_cg(&box[sibling]));   // L1-bypassing load, ordered after the atomic
-            store_box_cg(&box[cur], mine);
+            store_box_cg(&box[cur], mine, l, rr);
             if (cur == 0u) break;
             me = cur;
             cur = parent[cur];

@@ -306,33 +306,43 @@ RT_HD BBox refit_node(uint8_t* nodes, const uint8_t* tris, uint32_t w, const BBo
 RT_HD bool bt_expandable(const BinaryTree& t, uint32_t ref) {
     return ref < (uint32_t)(t.n - 1) && bt_count(t, ref) > (uint32_t)kLeafMaxTris;
 }
-RT_HD float bt_area(const BinaryTree& t, uint32_t ref) {
-    const float a = bbox_half_area(t.box[ref]);
+RT_HD float box_area(const BBox& b) {
+    const float a = bbox_half_area(b);
     return a >= 0.0f ? a : 0.0f;   // NaN / negative -> 0
 }
+// child references of an inner binary node, stored as bit patterns in the pad words of its box record
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t box_left(const BBox& b) { return __float_as_uint(b.pad0); }
+RT_HD uint32_t box_right(const BBox& b) { return __float_as_uint(b.pad1); }
+#else
+RT_HD uint32_t box_left(const BBox& b) { union { float f; uint32_t u; } c; c.f = b.pad0; return c.u; }
+RT_HD uint32_t box_right(const BBox& b) { union { float f; uint32_t u; } c; c.f = b.pad1; return c.u; }
+#endif
 RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, const float* __restrict__ verts,
                          int64_t n_verts, const int32_t* __restrict__ faces) {
     uint32_t ref[8];
     float area[8];
     bool inner[8];
+    BBox cb[8];
     int k = 0;
     const uint32_t src = load_cg_u32(&o.wide_src[w]);
     const BBox nb = t.box[src];
     if (t.n <= (int64_t)kLeafMaxTris) {
         // whole mesh fits one leaf slot (n = 1..3): root with a single leaf child
-        ref[0] = src; area[0] = 0.0f; inner[0] = false; k = 1;
+        ref[0] = src; area[0] = 0.0f; inner[0] = false; cb[0] = nb; k = 1;
     } else {
-        ref[0] = t.left[src]; ref[1] = t.right[src]; k = 2;
-        for (int i = 0; i < 2; ++i) { inner[i] = bt_expandable(t, ref[i]); area[i] = bt_area(t, ref[i]); }
+        // the box record of an inner binary node carries its two child references in the pad words
+        // (written by the refit pass), so expanding a child costs no extra dependent load
+        ref[0] = box_left(nb); ref[1] = box_right(nb); k = 2;
+        for (int i = 0; i < 2; ++i) { cb[i] = t.box[ref[i]]; inner[i] = bt_expandable(t, ref[i]); area[i] = box_area(cb[i]); }
         while (k < 8) {
             int best = -1; float ba = -1.0f;
             for (int i = 0; i < k; ++i)
                 if (inner[i] && area[i] > ba) { best = i; ba = area[i]; }
             if (best < 0) break;
-            const uint32_t b = ref[best];
-            const uint32_t l = t.left[b], r = t.right[b];
-            ref[best] = l; inner[best] = bt_expandable(t, l); area[best] = bt_area(t, l);
-            ref[k] = r; inner[k] = bt_expandable(t, r); area[k] = bt_area(t, r);
+            const uint32_t l = box_left(cb[best]), r = box_right(cb[best]);
+            ref[best] = l; cb[best] = t.box[l]; inner[best] = bt_expandable(t, l); area[best] = box_area(cb[best]);
+            ref[k] = r; cb[k] = t.box[r]; inner[k] = bt_expandable(t, r); area[k] = box_area(cb[k]);
             ++k;
         }
         // free slots left: split multi-triangle leaves (largest box first) so that each triangle
@@ -342,18 +352,14 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             for (int i = 0; i < k; ++i)
                 if (!inner[i] && ref[i] < (uint32_t)(t.n - 1) && area[i] > ba) { best = i; ba = area[i]; }
             if (best < 0) break;
-            const uint32_t b = ref[best];
-            const uint32_t l = t.left[b], r = t.right[b];
-            ref[best] = l; inner[best] = false; area[best] = bt_area(t, l);
-            ref[k] = r; inner[k] = false; area[k] = bt_area(t, r);
+            const uint32_t l = box_left(cb[best]), r = box_right(cb[best]);
+            ref[best] = l; cb[best] = t.box[l]; inner[best] = false; area[best] = box_area(cb[best]);
+            ref[k] = r; cb[k] = t.box[r]; inner[k] = false; area[k] = box_area(cb[k]);
             ++k;
         }
     }
-    // child boxes, kinds
-    BBox cb[8];
     uint32_t n_inner = 0, n_tris = 0;
     for (int i = 0; i < k; ++i) {
-        cb[i] = t.box[ref[i]];
         if (inner[i]) ++n_inner; else n_tris += bt_count(t, ref[i]);
     }
     // greedy slot assignment: child i goes to the free slot whose octant direction agrees
