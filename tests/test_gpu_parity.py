@@ -227,8 +227,16 @@ def test_input_validation(cuda_device):
         r.intersects_any(o.double(), o.double())
     with pytest.raises(ValueError):
         r.intersects_any(o, torch.zeros(5, 3, device=cuda_device))
-    with pytest.raises(ValueError):
-        r.intersects_any(torch.zeros(2, 2, 2, 2, 3, device=cuda_device), torch.zeros(2, 2, 2, 2, 3, device=cuda_device))
+    # more than 3 batch dims (reference limit MAX_SIZE_LENGTH = 4, silently wrong there): merged, same answers
+    o5, d5 = synth.random_rays(2 * 3 * 4 * 5, seed=3, device=cuda_device, box=True)
+    o5 = (o5 * 2).reshape(2, 3, 4, 5, 3); d5 = d5.reshape(2, 3, 4, 5, 3)
+    a5 = r.intersects_closest(o5, d5)
+    b5 = r.intersects_closest(o5.reshape(-1, 3), d5.reshape(-1, 3))
+    assert a5[0].shape == (2, 3, 4, 5) and a5[3].shape == (2, 3, 4, 5, 3)
+    for x, y in zip(a5, b5):
+        assert torch.equal(x.reshape(y.shape), y)
+    a5t = r.intersects_count(o5.transpose(0, 3), d5.transpose(0, 3))                 # non-mergeable strides -> copy
+    assert torch.equal(a5t, r.intersects_count(o5, d5).transpose(0, 3))
     with pytest.raises(ValueError):
         RayMeshIntersector(foo=1)
     with pytest.raises(ValueError):

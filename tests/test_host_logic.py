@@ -26,8 +26,9 @@ def test_ray_desc_right_aligns_shape_and_strides_like_fill_array():
 
 
 def test_ray_desc_rejects_what_the_reference_silently_mishandles():
-    with pytest.raises(ValueError):
-        ops.make_ray_desc(torch.zeros(2, 2, 2, 2, 3), torch.zeros(2, 2, 2, 2, 3))      # > 3 batch dims
+    # > 3 batch dims: the reference silently mis-indexes (ray.cpp:151-159); here the surplus leading dims are merged
+    rd, batch = ops.make_ray_desc(torch.zeros(2, 5, 2, 2, 3), torch.zeros(2, 5, 2, 2, 3))
+    assert batch == (2, 5, 2, 2) and rd.nray == 40 and list(rd.shape) == [10, 2, 2, 3] and list(rd.o_stride) == [12, 6, 3, 1]
     with pytest.raises(ValueError):
         ops.make_ray_desc(torch.zeros(4, 2), torch.zeros(4, 2))                        # last dim != 3
     with pytest.raises(ValueError):

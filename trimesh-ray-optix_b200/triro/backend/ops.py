@@ -178,9 +178,16 @@ def make_ray_desc(origins: torch.Tensor, dirs: torch.Tensor | None) -> Tuple[Ray
     if dirs is not None and dirs.device != origins.device:
         raise ValueError("origins and directions must be on the same device")
     batch = tuple(origins.shape[:-1])
+    keep = None
     if len(batch) > MAX_BATCH_DIMS:
-        raise ValueError(f"at most {MAX_BATCH_DIMS} batch dimensions are supported (reference MAX_SIZE_LENGTH=4)")
+        # The reference keeps only the last 4 sizes/strides and silently reads wrong data (ray.cpp:151-159,
+        # SURVEY A.1).  Here the surplus leading dimensions are merged into one (a view when the strides allow
+        # it, otherwise a copy); results are reshaped back to the full batch shape by the callers.
+        origins = origins.reshape(-1, *origins.shape[-3:])
+        dirs = dirs.reshape(-1, *dirs.shape[-3:]) if dirs is not None else None
+        keep = (origins, dirs)
     rd = RayDesc()
+    rd._keepalive = keep
     n = 1
     for s in batch:
         n *= s
