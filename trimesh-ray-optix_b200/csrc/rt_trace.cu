@@ -532,7 +532,8 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
         RT_REQUIRE(per_sm > 0, RT_ERR_CUDA, "%s: kernel does not fit an SM", fn);
     }
     int64_t grid = (int64_t)dev.sm_count * per_sm;
-    const int64_t need = (rays->nray + kTraceThreads - 1) / kTraceThreads;
+    const int64_t rays_per_cta = (int64_t)kTraceThreads * env_int("TRIRO_GRID_DIV", 1, 1, 64);
+    const int64_t need = (rays->nray + rays_per_cta - 1) / rays_per_cta;
     if (grid > need) grid = need;
     if (queued) k_trace<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
     else k_trace<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
