@@ -32,6 +32,8 @@ extern "C" {
 
 /* reference: LaunchParams.h:8-9 */
 #define RT_MAX_ANYHIT_SIZE 8
+/* the all-hits entry points accept max_hits up to this limit (the reference's cap of 8 is the default) */
+#define RT_MAX_HITS_LIMIT 64
 #define RT_MAX_SIZE_LENGTH 4
 /* reference: tmin = 0, tmax = 1e7 on every optixTrace, shaders.cu:86,112,163,191,238 */
 #define RT_TMAX_DEFAULT 1.0e7f
@@ -93,6 +95,10 @@ const char* rt_last_error(void);
 int rt_abi_version(void);
 /* number of SMs of the current device (0 when there is no device) */
 int rt_device_sm_count(void);
+/* Far end of the ray interval (0, tmax) used by every trace entry point called from this host thread afterwards.
+ * Default RT_TMAX_DEFAULT = 1e7, the reference's hard-coded optixTrace tmax (shaders.cu:86). */
+int rt_set_tmax(float tmax);
+float rt_get_tmax(void);
 
 /* ---- BVH build: replaces OptixAccelStructureWrapperCPP::buildAccelStructure
  *      (ray.cpp:27-100) = optixAccelComputeMemoryUsage + optixAccelBuild + optixAccelCompact.
@@ -154,7 +160,7 @@ int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* workspace,
 
 /* ---- All hits: replaces intersectsLocation (ray.cpp:324-378; shaders.cu:196-246), i.e. the
  *      reference's count pass + clamp/cumsum (ray.cpp:333-342) + second traversal, in ONE traversal:
- *      step 1 traces once, storing up to max_hits (<= RT_MAX_ANYHIT_SIZE) hits per ray into
+ *      step 1 traces once, storing up to max_hits (<= RT_MAX_HITS_LIMIT, reference: 8) hits per ray into
  *      `staging` (nray * max_hits * 16 bytes: tri, x, y, z) and the clamped count per ray, then
  *      scans the counts; step 2 packs them by ray. */
 int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_bytes, size_t* workspace_bytes);

@@ -53,10 +53,13 @@ def test_size_queries_and_argument_validation(lib):
     assert lib.rt_bvh_sizes(0, 0, C.byref(ws), C.byref(blob)) == 0 and blob.value >= 256 + 80
     st, w2 = C.c_size_t(), C.c_size_t()
     assert lib.rt_allhits_sizes(1000, 8, C.byref(st), C.byref(w2)) == 0 and st.value == 1000 * 8 * 16
-    assert lib.rt_allhits_sizes(1000, 9, C.byref(st), C.byref(w2)) == -1           # MAX_ANYHIT_SIZE = 8
+    assert lib.rt_allhits_sizes(1000, 65, C.byref(st), C.byref(w2)) == -1          # RT_MAX_HITS_LIMIT = 64 (reference default 8)
     assert lib.rt_compact_sizes(5000, C.byref(w2)) == 0 and w2.value >= 256 + 2 * 8 * 3
     assert lib.rt_sort_sizes(10_000, C.byref(w2)) == 0 and w2.value >= 10_000 * 12
     assert lib.rt_abi_version() == 1
+    assert lib.rt_get_tmax() == 1.0e7                                               # reference: shaders.cu:86
+    assert lib.rt_set_tmax(-1.0) == -1 and lib.rt_get_tmax() == 1.0e7
+    assert lib.rt_set_tmax(25.0) == 0 and lib.rt_get_tmax() == 25.0 and lib.rt_set_tmax(1.0e7) == 0
 
 
 def test_compute_entry_points_fail_loudly_without_a_device(lib):

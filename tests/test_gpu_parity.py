@@ -677,3 +677,30 @@ def test_fused_pinhole_generation_matches_explicit_rays(cuda_device):
     normals = torch.from_numpy(v).to(cuda_device)                      # unit sphere: vertex normal = position
     n = r.interpolate(normals, c[3], c[5])
     assert float((n - c[4]).abs().max()) < 1e-5                        # interpolated position attribute == hit location
+
+
+def test_tmax_and_max_hits_extensions_keep_reference_defaults(cuda_device):
+    """tmax (reference: hard-coded 1e7, shaders.cu:86) and max_hits (reference: 8,
+    LaunchParams.h:8) are constructor keywords; two intersectors with different settings coexist."""
+    n = 40
+    quads = []
+    for k in range(n):
+        z = -k * 0.1
+        quads += [[-1, -1, z], [1, -1, z], [1, 1, z], [-1, 1, z]]
+    v = torch.tensor(quads, dtype=torch.float32)
+    f = torch.tensor([[4 * k + a, 4 * k + b, 4 * k + c] for k in range(n) for (a, b, c) in ((0, 1, 2), (0, 2, 3))], dtype=torch.int32)
+    ref = RayMeshIntersector(vertices=v, faces=f)                               # reference defaults
+    short = RayMeshIntersector(vertices=v, faces=f, tmax=5.55, max_hits=16)     # reaches z >= -0.55 from z = 5
+    o = torch.tensor([[0.3, 0.2, 5.0]], device=cuda_device); d = torch.tensor([[0.0, 0.0, -1.0]], device=cuda_device)
+    assert ref.intersects_count(o, d).tolist() == [40] and short.intersects_count(o, d).tolist() == [6]
+    assert ref.intersects_count(o, d).tolist() == [40]                          # switching back and forth
+    assert len(ref.intersects_location(o, d)[0]) == 8
+    far = RayMeshIntersector(vertices=v, faces=f, max_hits=16)
+    loc, ri, ti = far.intersects_location(o, d)
+    assert len(loc) == 16 and len(set(ti.tolist())) == 16
+    assert short.intersects_any(torch.tensor([[0.3, 0.2, 6.0]], device=cuda_device), d).tolist() == [False]   # first quad at t = 6 > tmax
+    assert ref.intersects_any(torch.tensor([[0.3, 0.2, 6.0]], device=cuda_device), d).tolist() == [True]
+    with pytest.raises(ValueError):
+        RayMeshIntersector(vertices=v, faces=f, max_hits=65)
+    with pytest.raises(ValueError):
+        RayMeshIntersector(vertices=v, faces=f, tmax=-1.0)

@@ -261,7 +261,7 @@ extern "C" int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* 
 extern "C" int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
                                   const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
                                   void* stream) {
-    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE, RT_ERR_INVALID,
+    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT, RT_ERR_INVALID,
                "rt_allhits_scatter: bad arguments");
     if (nray == 0) return RT_OK;
     RT_REQUIRE(count_clamped && staging && workspace, RT_ERR_INVALID, "rt_allhits_scatter: null input");

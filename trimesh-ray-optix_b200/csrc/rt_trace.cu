@@ -469,6 +469,8 @@ static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t n
     return nray < ((int64_t)1 << 31) ? kGeneral32 : kGeneral;
 }
 
+static thread_local float g_tmax = RT_TMAX_DEFAULT;
+
 static int env_int(const char* name, int fallback, int lo, int hi) {
     const char* e = getenv(name);
     int v = e ? atoi(e) : fallback;
@@ -510,7 +512,7 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
         p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
         p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
     }
-    p.tmax = RT_TMAX_DEFAULT;
+    p.tmax = g_tmax;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
     RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
@@ -544,6 +546,13 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
 }  // namespace rt
 
 using namespace rt;
+
+extern "C" int rt_set_tmax(float tmax) {
+    RT_REQUIRE(tmax > 0.0f, RT_ERR_INVALID, "rt_set_tmax: tmax must be positive (got %g)", (double)tmax);
+    g_tmax = tmax;
+    return RT_OK;
+}
+extern "C" float rt_get_tmax(void) { return g_tmax; }
 
 extern "C" int rt_trace_any(const void* blob, const rt_ray_desc* rays, uint8_t* hit, void* scratch, void* stream) {
     RT_REQUIRE(hit || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_any: null output");
@@ -628,7 +637,7 @@ size_t scan_workspace_bytes(int64_t n);
 }
 
 extern "C" int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_bytes, size_t* workspace_bytes) {
-    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE && staging_bytes && workspace_bytes,
+    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT && staging_bytes && workspace_bytes,
                RT_ERR_INVALID, "rt_allhits_sizes: bad arguments");
     *staging_bytes = (size_t)nray * (size_t)max_hits * 16u;
     *workspace_bytes = scan_workspace_bytes(nray);
@@ -638,7 +647,7 @@ extern "C" int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_byte
 extern "C" int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, int32_t* count_clamped,
                                 void* staging, void* workspace, size_t workspace_bytes, int64_t* total_dev,
                                 void* scratch, void* stream) {
-    RT_REQUIRE(max_hits >= 1 && max_hits <= RT_MAX_ANYHIT_SIZE, RT_ERR_INVALID, "rt_allhits_trace: max_hits out of range");
+    RT_REQUIRE(max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT, RT_ERR_INVALID, "rt_allhits_trace: max_hits out of range");
     RT_REQUIRE(total_dev != nullptr, RT_ERR_INVALID, "rt_allhits_trace: null total");
     RT_REQUIRE((count_clamped && staging && workspace) || (rays && rays->nray == 0), RT_ERR_INVALID,
                "rt_allhits_trace: null buffer");

@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import struct
+import threading
 from typing import Tuple
 
 import torch
@@ -59,6 +60,8 @@ def _declare(lib):
         "rt_last_error": (C.c_char_p, []),
         "rt_abi_version": (ci, []),
         "rt_device_sm_count": (ci, []),
+        "rt_set_tmax": (ci, [C.c_float]),
+        "rt_get_tmax": (C.c_float, []),
         "rt_bvh_sizes": (ci, [i64, i64, psz, psz]),
         "rt_bvh_build": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
         "rt_bvh_refit_sizes": (ci, [i64, psz]),
@@ -141,6 +144,20 @@ def _check(rc: int, what: str):
         raise RuntimeError(f"{what}: {msg} (status {rc})")
 
 
+TMAX_DEFAULT = 1.0e7        # reference: tmax of every optixTrace, shaders.cu:86
+MAX_HITS_LIMIT = 64
+_tls = threading.local()
+
+
+def _apply_tmax(accel) -> None:
+    """The C ABI keeps the far end of the ray interval per host thread (rt_set_tmax); push the accel's value when it
+    differs from what this thread set last.  Default 1e7 = the reference's hard-coded value."""
+    t = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT))
+    if getattr(_tls, "tmax", TMAX_DEFAULT) != t:
+        _check(get_module().rt_set_tmax(t), "rt_set_tmax")
+        _tls.tmax = t
+
+
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -208,6 +225,7 @@ class AccelStructure:
     ray.h:11-16, whose GAS is an opaque buffer owned by C++)."""
 
     def __init__(self):
+        self.tmax: float = TMAX_DEFAULT      # rays are clipped to (0, tmax)
         self.blob: torch.Tensor | None = None
         self.header: dict | None = None
         self.build_ms: float | None = None
@@ -326,6 +344,7 @@ def intersects_any(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -
     """Bool[*b]: does each ray hit anything with 0 < t < 1e7 (reference ops.py:84-101)."""
     tensor_input_check(origins, dirs)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
@@ -339,6 +358,7 @@ def intersects_first(accel_structure, origins: torch.Tensor, dirs: torch.Tensor)
     """Int32[*b]: index of the nearest hit triangle or -1 (reference ops.py:104-119)."""
     tensor_input_check(origins, dirs)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
@@ -353,6 +373,7 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
     (reference ops.py:122-149, ray.cpp:231-289)."""
     tensor_input_check(origins, dirs)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
@@ -371,6 +392,7 @@ def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int,
     test/performance_test.py:10-20) generated inside the kernel: no ray tensors are built or read.
     Returns (hit[h,w], front[h,w], tri[h,w], loc[h,w,3], uv[h,w,2])."""
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     dev = blob.device
     cam = Pinhole()
     cam.width, cam.height, cam.focal = int(width), int(height), float(focal)
@@ -424,6 +446,7 @@ def intersects_count(accel_structure, origins: torch.Tensor, dirs: torch.Tensor)
     """Int32[*b]: number of triangles hit with 0 < t < 1e7 (reference ops.py:152-168)."""
     tensor_input_check(origins, dirs)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
@@ -440,6 +463,7 @@ def intersects_location(accel_structure, origins: torch.Tensor, dirs: torch.Tens
     tensor_input_check(origins, dirs)
     lib = get_module()
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
     n = rd.nray
@@ -467,6 +491,7 @@ def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, a
     (contain Bool[*b], broken Bool[*b], flags Int32[2] = [any(inside_aabb), any(broken)])."""
     tensor_input_check(points)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, batch = make_ray_desc(points, None)
     dev = points.device
     d3 = (C.c_float * 3)(*[float(x) for x in direction])
@@ -485,6 +510,7 @@ def trace_stats(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, mode
     """Instrumented traversal: mean BVH8 nodes / triangles fetched per ray (roofline input)."""
     tensor_input_check(origins, dirs)
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
@@ -504,6 +530,7 @@ def host_closest(accel_structure, origins_host: torch.Tensor, dirs_host: torch.T
     [3]/[1,3] origin shared by all rays.  Returns a dict of host tensors."""
     lib = get_module()
     blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
     dev = blob.device
     d = dirs_host
     if d.is_cuda or d.dtype != torch.float32 or not d.is_contiguous() or d.shape[-1] != 3:

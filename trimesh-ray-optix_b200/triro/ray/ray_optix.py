@@ -34,7 +34,14 @@ class RayMeshIntersector:
             faces = kwargs["faces"]
         else:
             raise ValueError("Either 'mesh' or 'vertices' and 'faces' must be provided.")
+        # Extensions: the reference hard-codes tmax = 1e7 (shaders.cu:86) and at most 8 hits per ray
+        # (LaunchParams.h:8); both stay the defaults.
+        self.tmax = float(kwargs.get("tmax", hops.TMAX_DEFAULT))
+        self.max_hits = int(kwargs.get("max_hits", hops.MAX_ANYHIT_SIZE))
+        if not (self.tmax > 0.0) or not (1 <= self.max_hits <= hops.MAX_HITS_LIMIT):
+            raise ValueError(f"tmax must be positive and 1 <= max_hits <= {hops.MAX_HITS_LIMIT}")
         self.as_wrapper = OptixAccelStructureWrapper()
+        self.as_wrapper._inner.tmax = self.tmax
         self.update_raw(vertices, faces)
 
     def update_raw(self, vertices: torch.Tensor, faces: torch.Tensor):
@@ -109,7 +116,7 @@ class RayMeshIntersector:
     def intersects_location(self, origins: torch.Tensor, directions: torch.Tensor
                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(loc[h,3], ray_idx[h], tri_idx[h]) for every hit, at most 8 per ray (reference :157-164)."""
-        return hops.intersects_location(self.as_wrapper, origins, directions)
+        return hops.intersects_location(self.as_wrapper, origins, directions, getattr(self, "max_hits", hops.MAX_ANYHIT_SIZE))
 
     def intersects_count(self, origins: torch.Tensor, directions: torch.Tensor) -> torch.Tensor:
         """Int32[*b] — number of triangles each ray crosses (reference :172-177)."""
@@ -119,7 +126,8 @@ class RayMeshIntersector:
                       multiple_hits: bool = True):
         """(tri_idx[h], ray_idx[h][, loc[h,3]]) (reference :191-223)."""
         if multiple_hits:
-            loc, ray_idx, tri_idx = hops.intersects_location(self.as_wrapper, origins, directions)
+            loc, ray_idx, tri_idx = hops.intersects_location(self.as_wrapper, origins, directions,
+                                                             getattr(self, "max_hits", hops.MAX_ANYHIT_SIZE))
             if return_locations:
                 return tri_idx, ray_idx, loc
             return tri_idx, ray_idx
