@@ -704,3 +704,18 @@ def test_tmax_and_max_hits_extensions_keep_reference_defaults(cuda_device):
         RayMeshIntersector(vertices=v, faces=f, max_hits=65)
     with pytest.raises(ValueError):
         RayMeshIntersector(vertices=v, faces=f, tmax=-1.0)
+
+
+@pytest.mark.parametrize("scale,offset", [(1e6, 0.0), (1e-6, 0.0), (1e4, 3e7)])
+def test_extreme_scales_and_offsets_on_the_gpu(cuda_device, scale, offset):
+    v, f = synth.icosphere(4)
+    v = (v.astype(np.float64) * scale + offset).astype(np.float32)
+    r = make(v, f)
+    assert hostsim.check_blob(r.as_wrapper.blob.cpu().numpy())[0] == 0
+    o, d = synth.random_rays(30_000, seed=11, box=True)
+    o = torch.from_numpy(((o.numpy().astype(np.float64) * 2.0) * scale + offset).astype(np.float32)).to(cuda_device)
+    d = d.to(cuda_device)
+    got = closest_to_numpy(r.intersects_closest(o, d))
+    check_closest_vs_mirror(got, oracle.OracleMesh(v, f), flat(o), flat(d))
+    ref = oracle.query(oracle.OracleMesh(v, f), flat(o), flat(d), oracle.MIRROR, want=("count",))
+    assert_bits_equal(r.intersects_count(o, d).cpu().numpy(), ref["count"], "count at extreme scale")

@@ -127,3 +127,22 @@ def test_refit_keeps_the_blob_conservative_and_results_exact(name):
     assert hostsim.check_blob(blob3)[0] == 0
     ref0 = oracle.query(oracle.OracleMesh(v, f, use_bvh=False), o, d, oracle.MIRROR)
     assert np.array_equal(hostsim.trace(blob3, "closest", o, d)["tri"], ref0["tri"])
+
+
+@pytest.mark.parametrize("scale,offset", [(1e6, 0.0), (1e-6, 0.0), (1.0, 1e4), (1e-3, -5e2), (1e4, 3e7)])
+def test_extreme_scales_and_offsets_stay_conservative(scale, offset):
+    """Quantised boxes and the padded slab test must stay conservative far from the unit cube: huge / tiny meshes and
+    meshes far from the origin (few mantissa bits left for the geometry).  Bit-exact against the brute-force mirror."""
+    v, f = synth.icosphere(3)
+    v = (v.astype(np.float64) * scale + offset).astype(np.float32)
+    blob = hostsim.build_blob(v, f)
+    assert hostsim.check_blob(blob)[0] == 0
+    o, d = synth.random_rays(3000, seed=11, box=True)
+    o = ((o.numpy().astype(np.float64) * 2.0) * scale + offset).astype(np.float32)
+    d = d.numpy()
+    ref = oracle.query(oracle.OracleMesh(v, f, use_bvh=False), o, d, oracle.MIRROR)
+    got = hostsim.trace(blob, "closest", o, d)
+    for k in ("hit", "front", "tri"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["loc"].view(np.uint32), ref["loc"].view(np.uint32))
+    assert np.array_equal(hostsim.trace(blob, "count", o, d)["count"], ref["count"])
