@@ -11,8 +11,9 @@
  * (triro/backend/ray.cpp:79) and optixTrace (triro/backend/shaders.cu:86,112,163,191,238).
  * It cannot be built or run here, and the reference's own tests (test/test.py) contain no
  * assertions.  This oracle therefore restates the SEMANTICS the reference's programs define
- * around those calls, and is pinned against the known answers K1-K7 of test/test.py (see
- * tests/test_oracle_known_answers.py):
+ * around those calls, and is pinned against the known answers K1-K7 of test/test.py, against the
+ * reference's published README figure assets/location.png and against a fixture produced by executing
+ * the reference's own Python host logic (see tests/test_oracle_known_answers.py, tests/golden/):
  *   - ray interval: tmin = 0, tmax = 1e7, open on both sides        shaders.cu:86,112,163,191,238
  *   - closest hit: min t; tri index; front = CCW seen from origin;
  *     loc = u*v1 + v*v2 + (1-u-v)*v0; uv = (1-u-v, u)                shaders.cu:137-153

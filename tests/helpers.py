@@ -50,3 +50,25 @@ def check_closest_vs_truth(got: dict, mesh: oracle.OracleMesh, o, d, max_graze_f
         # uv are O(1) weights; tolerance scales with ray length / triangle size (binary32 conditioning)
         assert err_uv <= 2e-3, f"uv error {err_uv:.3e}"
     return ref, graze
+
+
+def compare_with_readme_figure(locs_800: np.ndarray):
+    """Compares an [800,800,3] hit-location image (zeros where nothing was hit) with the plot area of the reference's
+    published README figure (tests/golden/readme_location_png.npz, made by tests/golden/make_location_fixture.py).
+    matplotlib's imshow clips RGB to [0,1] and resamples 800 px to ~370 px, hence the tolerances.
+    Returns (mask IoU, mean abs colour difference on the disc)."""
+    import os
+
+    import torch
+    import torch.nn.functional as F
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "readme_location_png.npz"))
+    ref = g["plot_area"].astype(np.float32) / 255.0                       # [370, 369, 3]
+    img = torch.from_numpy(np.clip(locs_800, 0.0, 1.0).astype(np.float32)).permute(2, 0, 1)[None]
+    small = F.interpolate(img, size=ref.shape[:2], mode="area")[0].permute(1, 2, 0).numpy()
+    m_ref = ref.sum(axis=2) > 0.16
+    m_got = small.sum(axis=2) > 0.16
+    iou = float((m_ref & m_got).sum() / max((m_ref | m_got).sum(), 1))
+    both = m_ref & m_got
+    diff = float(np.abs(ref[both] - small[both]).mean())
+    return iou, diff

@@ -719,3 +719,21 @@ def test_extreme_scales_and_offsets_on_the_gpu(cuda_device, scale, offset):
     check_closest_vs_mirror(got, oracle.OracleMesh(v, f), flat(o), flat(d))
     ref = oracle.query(oracle.OracleMesh(v, f), flat(o), flat(d), oracle.MIRROR, want=("count",))
     assert_bits_equal(r.intersects_count(o, d).cpu().numpy(), ref["count"], "count at extreme scale")
+
+
+def test_readme_quickstart_reproduces_the_reference_published_figure(cuda_device):
+    """README.md:24-51 run verbatim (modulo matplotlib) against the reference's published result assets/location.png
+    (fixture tests/golden/readme_location_png.npz): same hit disc, same location colours."""
+    from helpers import compare_with_readme_figure
+
+    v, f = synth.icosphere(3)                                                   # trimesh.creation.icosphere()
+    intersector = make(v, f)
+    y, x = torch.meshgrid([torch.linspace(1, -1, 800), torch.linspace(-1, 1, 800)], indexing="ij")
+    z = -torch.ones_like(x)
+    ray_directions = torch.stack([x, y, z], dim=-1).cuda()
+    ray_origins = torch.Tensor([0, 0, 3]).cuda().broadcast_to(ray_directions.shape)
+    hit, front, ray_idx, tri_idx, location, uv = intersector.intersects_closest(ray_origins, ray_directions, stream_compaction=True)
+    locs = torch.zeros((800, 800, 3)).cuda()
+    locs[hit] = location
+    iou, diff = compare_with_readme_figure(locs.cpu().numpy())
+    assert iou > 0.985 and diff < 0.01, (iou, diff)
