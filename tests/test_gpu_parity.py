@@ -737,3 +737,26 @@ def test_readme_quickstart_reproduces_the_reference_published_figure(cuda_device
     locs[hit] = location
     iou, diff = compare_with_readme_figure(locs.cpu().numpy())
     assert iou > 0.985 and diff < 0.01, (iou, diff)
+
+
+@pytest.mark.parametrize("tilt", [0.0, 0.3])
+def test_watertight_no_leaks_on_the_gpu(cuda_device, tilt):
+    """Rays aimed exactly at the vertices, edge midpoints and cell centres of a flat 128 x 128 grid: every one must hit
+    (no cracks between triangles that share an edge or a vertex), bit-identical to the mirror."""
+    n = 128
+    v, f = synth.heightfield(n, n, amplitude=0.0)
+    xs = np.linspace(-1, 1, 2 * n + 1, dtype=np.float64)[1:-1]
+    gx, gy = np.meshgrid(xs, xs, indexing="xy")
+    targets = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1)
+    origins = targets + np.array([tilt, -0.5 * tilt, 1.0]) * 2.0
+    o = torch.from_numpy(origins.astype(np.float32)).to(cuda_device)
+    d = torch.from_numpy((targets - origins).astype(np.float32)).to(cuda_device)
+    r = make(v, f)
+    hit, front, tri, loc, uv = r.intersects_closest(o, d)
+    assert bool(hit.all()), f"{int((~hit).sum())} rays leaked"
+    assert float(loc[:, 2].abs().max()) < 1e-6 and bool(front.all())
+    got = closest_to_numpy((hit, front, tri, loc, uv))
+    check_closest_vs_mirror(got, oracle.OracleMesh(v, f), flat(o), flat(d))
+    assert int(r.intersects_count(o, d).min()) >= 1
+    # the same through the queued schedule (materialised per-ray origins already are) and the any-hit early exit
+    assert bool(r.intersects_any(o, d).all())
