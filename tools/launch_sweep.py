@@ -12,6 +12,8 @@ cam_mat = torch.tensor([[5.6272650e-01, 2.7091104e-01, 7.8099048e-01], [8.260232
 scene = sys.argv[1] if len(sys.argv) > 1 else "icosphere"
 if scene == "icosphere":
     v, f = synth.icosphere(7); dist = 3.0
+elif scene == "tiny":
+    v, f = synth.icosphere(0); dist = 3.0
 elif scene == "soup":
     v, f = synth.triangle_soup(1_000_000, seed=3); dist = 3.0
 else:
