@@ -4,6 +4,7 @@
 // rays live in host memory pays H2D + trace + D2H back to back, the way test/performance_test.py
 // moves its result to the CPU.  This entry point pipelines the three over fixed-size ray chunks on
 // kSlots private streams so the PCIe copies of chunk i+1 / i-1 overlap the traversal of chunk i.
+#include <stdio.h>
 #include <stdlib.h>
 #include "rt_api.h"
 
@@ -80,6 +81,15 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
     // crossing PCIe almost immediately; the D2H direction is the bottleneck of the whole call
     const int64_t ramp0 = env_i64("TRIRO_HOST_RAMP", 1 << 16, 1024, chunk);
     int64_t m = 0;
+#ifdef RT_HOST_TIMELINE   // debugging aid (-DRT_HOST_TIMELINE): per-chunk event timeline printed to stderr
+    static cudaEvent_t tl[64][4];
+    static bool tl_made = false;
+    if (!tl_made) { for (auto& row : tl) for (auto& ev : row) cudaEventCreate(&ev); tl_made = true; }
+    int64_t tl_m[64]; int tl_n = 0;
+#define RT_TL_MARK(k) if (c < 64) cudaEventRecord(tl[c][k], st)
+#else
+#define RT_TL_MARK(k) ((void)0)
+#endif
     for (int64_t c = 0, first = 0; rc == RT_OK && first < nray; ++c, first += m) {
         const int s = (int)(c % kSlots);
         uint8_t* w = base + (size_t)s * lay.bytes;
@@ -90,10 +100,15 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
         float* d_o = reinterpret_cast<float*>(w + lay.origins);
         float* d_d = reinterpret_cast<float*>(w + lay.directions);
         cudaError_t e = cudaSuccess;
+#ifdef RT_HOST_TIMELINE
+        if (c < 64) { tl_m[c] = m; tl_n = (int)c + 1; }
+#endif
+        RT_TL_MARK(0);
         if (origins_broadcast) e = cudaMemcpyAsync(d_o, h_origins, 12, cudaMemcpyHostToDevice, st);
         else e = cudaMemcpyAsync(d_o, h_origins + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, h_directions + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        RT_TL_MARK(1);
         rt_ray_desc rd;
         rd.nray = m;
         rd.shape[0] = 1; rd.shape[1] = 1; rd.shape[2] = m; rd.shape[3] = 3;
@@ -104,16 +119,28 @@ extern "C" int rt_host_trace_closest(const void* blob, int64_t nray, const float
                               reinterpret_cast<float*>(w + lay.loc), reinterpret_cast<float*>(w + lay.uv),
                               w + lay.scratch, st);
         if (rc != RT_OK) break;
+        RT_TL_MARK(2);
         e = cudaMemcpyAsync(h_hit + first, w + lay.hit, (size_t)m, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_front + first, w + lay.front, (size_t)m, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_tri_idx + first, w + lay.tri, (size_t)m * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_loc + 3 * first, w + lay.loc, (size_t)m * 12, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_uv + 2 * first, w + lay.uv, (size_t)m * 8, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) { rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: D2H copy failed: %s", cudaGetErrorString(e)); break; }
+        RT_TL_MARK(3);
     }
     for (int i = 0; i < made && i < kSlots; ++i) {
         const cudaError_t e = cudaStreamSynchronize(streams[i]);
         if (e != cudaSuccess && rc == RT_OK) rc = set_error(RT_ERR_CUDA, "rt_host_trace_closest: %s", cudaGetErrorString(e));
     }
+#ifdef RT_HOST_TIMELINE
+    if (getenv("TRIRO_HOST_TIMELINE")) {
+        for (int c = 0; c < tl_n; ++c) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tl[0][0], tl[c][k]);
+            fprintf(stderr, "chunk %2d %8lld rays: h2d %7.3f..%7.3f  kernel ..%7.3f  d2h ..%7.3f ms\n", c, (long long)tl_m[c],
+                    t[0], t[1], t[2], t[3]);
+        }
+    }
+#endif
     return rc;
 }
