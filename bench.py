@@ -195,6 +195,11 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: keep this rank's pinned buffers and copy submission on the GPU's own NUMA node
+    all_cpus = os.sched_getaffinity(0)
+    from triro.distributed import bind_to_device_cpus
+
+    local_cpus = None if os.environ.get("TRIRO_BENCH_NO_BIND") else bind_to_device_cpus(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -303,7 +308,9 @@ def run_b200(args):
         }
         if bcast_ms is not None:
             line["bvh_build_plus_broadcast_ms"] = bcast_ms
+        line["host_cpus_bound"] = len(local_cpus) if local_cpus else None
         if world == 1:
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline uses every host core
             val, cores, sample, secs = cpu_closest(v, f, np.array([[0.0, 0.0, 3.0]], np.float32), d.reshape(-1, 3).cpu().numpy(),
                                                    sample=2_000_000)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,

@@ -22,6 +22,32 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_device_cpus(device_index: int) -> List[int] | None:
+    """Pin the calling thread (and the threads / pinned host allocations it makes from now on) to the CPU cores
+    that are local to CUDA device `device_index` (same NUMA node / PCIe root), via NVML's ideal CPU affinity.
+    With one process per GPU on a two-socket host this keeps each rank's pinned buffers and copy submission off the
+    inter-socket link, which is what the host-buffer path (rt_host_trace_closest) is bound by at 8 ranks.
+    Returns the CPU list, or None when NVML / the mapping is unavailable (nothing changed)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of n rays owned by `rank`: ceil(n / world) rays per rank."""
     per = (n + world - 1) // world if world > 0 else n
