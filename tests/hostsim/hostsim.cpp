@@ -127,6 +127,122 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     return 0;
 }
 
+// EXPERIMENT HOOK: same as hs_build, but the binary topology comes from a top-down binned-SAH
+// builder (16 bins, centroid bounds) instead of Morton order + Karras.  Used to measure how much
+// of the traversal cost is tree quality (tools/sah_probe.py); the product builds LBVH only.
+namespace {
+struct SahBuilder {
+    const std::vector<BBox>& tb; std::vector<uint32_t>& order;
+    std::vector<uint32_t>&left, &right, &first, &last; uint32_t next = 0; int64_t n;
+    // returns ref of the subtree over order[lo..hi] (inclusive)
+    uint32_t build(uint32_t lo, uint32_t hi, uint32_t self) {
+        if (lo == hi) return (uint32_t)(n - 1) + lo;
+        float cl[3] = {INFINITY, INFINITY, INFINITY}, ch[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = lo; i <= hi; ++i) {
+            const BBox& b = tb[order[i]];
+            const float c[3] = {0.5f * (b.lx + b.hx), 0.5f * (b.ly + b.hy), 0.5f * (b.lz + b.hz)};
+            for (int a = 0; a < 3; ++a) { cl[a] = fminf(cl[a], c[a]); ch[a] = fmaxf(ch[a], c[a]); }
+        }
+        constexpr int NB = 16;
+        float best = INFINITY; int best_axis = -1, best_split = 0;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = ch[a] - cl[a];
+            if (!(ext > 0.0f)) continue;
+            BBox bb[NB]; uint32_t cnt[NB] = {0};
+            for (auto& b : bb) { b.lx = b.ly = b.lz = INFINITY; b.hx = b.hy = b.hz = -INFINITY; b.pad0 = b.pad1 = 0; }
+            for (uint32_t i = lo; i <= hi; ++i) {
+                const BBox& b = tb[order[i]];
+                const float c = a == 0 ? 0.5f * (b.lx + b.hx) : a == 1 ? 0.5f * (b.ly + b.hy) : 0.5f * (b.lz + b.hz);
+                int k = (int)((c - cl[a]) / ext * NB); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
+                bb[k] = bbox_union(bb[k], b); ++cnt[k];
+            }
+            float la[NB], ra[NB]; uint32_t lc[NB], rc[NB];
+            BBox acc = bb[0]; uint32_t c = 0;
+            for (int k = 0; k < NB; ++k) { if (k == 0) acc = bb[0]; else acc = bbox_union(acc, bb[k]); c += cnt[k]; la[k] = c ? bbox_half_area(acc) : 0.f; lc[k] = c; }
+            c = 0;
+            for (int k = NB - 1; k >= 0; --k) { if (k == NB - 1) acc = bb[k]; else acc = bbox_union(acc, bb[k]); c += cnt[k]; ra[k] = c ? bbox_half_area(acc) : 0.f; rc[k] = c; }
+            for (int k = 0; k + 1 < NB; ++k) {
+                if (lc[k] == 0 || rc[k + 1] == 0) continue;
+                const float cost = la[k] * lc[k] + ra[k + 1] * rc[k + 1];
+                if (cost < best) { best = cost; best_axis = a; best_split = k; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) mid = lo + (hi - lo) / 2;      // all centroids equal: split in the middle
+        else {
+            const int a = best_axis; const float ext = ch[a] - cl[a];
+            auto it = std::stable_partition(order.begin() + lo, order.begin() + hi + 1, [&](uint32_t id) {
+                const BBox& b = tb[id];
+                const float c = a == 0 ? 0.5f * (b.lx + b.hx) : a == 1 ? 0.5f * (b.ly + b.hy) : 0.5f * (b.lz + b.hz);
+                int k = (int)((c - cl[a]) / ext * 16); if (k >= 16) k = 15; if (k < 0) k = 0;
+                return k <= best_split; });
+            mid = (uint32_t)(it - order.begin()) - 1;
+            if (mid < lo || mid >= hi) mid = lo + (hi - lo) / 2;
+        }
+        first[self] = lo; last[self] = hi;
+        const uint32_t ls = (mid > lo) ? ++next : 0, rs = (hi > mid + 1) ? ++next : 0;
+        left[self] = build(lo, mid, ls);
+        right[self] = build(mid + 1, hi, rs);
+        return self;
+    }
+};
+}  // namespace
+
+extern "C" int hs_build_sah(const float* verts, int64_t nv, const int32_t* faces, int64_t n, uint8_t* blob, size_t blob_bytes) {
+    const Layout lay = layout(n);
+    if (blob_bytes < lay.total || n < 2) return -3;
+    memset(blob, 0, lay.total);
+    rt_blob_header h;
+    memset(&h, 0, sizeof(h));
+    h.magic = RT_BLOB_MAGIC; h.abi_version = RT_ABI_VERSION; h.n_tris = (uint32_t)n; h.n_nodes_cap = lay.node_cap;
+    h.tris_offset = lay.tris_offset; h.nodes_offset = lay.nodes_offset; h.parents_offset = lay.parents_offset;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    std::vector<BBox> tb((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        float v[9]; tri_verts(verts, nv, faces, i, v);
+        tb[i] = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+        lo[0] = fminf(lo[0], tb[i].lx); lo[1] = fminf(lo[1], tb[i].ly); lo[2] = fminf(lo[2], tb[i].lz);
+        hi[0] = fmaxf(hi[0], tb[i].hx); hi[1] = fmaxf(hi[1], tb[i].hy); hi[2] = fmaxf(hi[2], tb[i].hz);
+    }
+    std::vector<uint32_t> vals((size_t)n);
+    std::iota(vals.begin(), vals.end(), 0u);
+    const size_t ni = (size_t)(n - 1);
+    std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni);
+    SahBuilder sb{tb, vals, left, right, first, last, 0, n};
+    sb.build(0, (uint32_t)(n - 1), 0);
+    // boxes bottom-up (post-order via explicit recursion on the finished topology)
+    std::vector<BBox> box((size_t)2 * n);
+    for (int64_t k = 0; k < n; ++k) box[(n - 1) + k] = tb[vals[k]];
+    std::vector<uint32_t> stack{0}; std::vector<uint32_t> post;
+    while (!stack.empty()) { const uint32_t c = stack.back(); stack.pop_back(); post.push_back(c);
+        if (left[c] < ni) stack.push_back(left[c]); if (right[c] < ni) stack.push_back(right[c]); }
+    for (auto it = post.rbegin(); it != post.rend(); ++it) {
+        const uint32_t c = *it;
+        box[c] = bbox_union(box[left[c]], box[right[c]]);
+        memcpy(&box[c].pad0, &left[c], 4); memcpy(&box[c].pad1, &right[c], 4);
+    }
+    std::vector<uint32_t> wide_src(lay.node_cap, 0);
+    uint32_t node_count = 1, tri_count = 0;
+    BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
+    t.box = box.data(); t.sorted_prim = vals.data();
+    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
+    o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
+    o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
+    uint32_t begin = 0, end = 1, depth = 0;
+    while (begin < end) {
+        for (uint32_t w = begin; w < end; ++w) collapse_node(t, o, w, verts, nv, faces);
+        ++depth;
+        begin = end;
+        end = node_count < lay.node_cap ? node_count : lay.node_cap;
+    }
+    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, vals.data(), verts, nv, faces);
+    h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
+    for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
+    h.node_overflow = node_count > lay.node_cap ? 1u : 0u;
+    memcpy(blob, &h, sizeof(h));
+    return 0;
+}
+
 // mode: 0 closest (writes hit/front/tri/loc/uv), 1 any (hit), 2 count (count).  stats[0..3] as rt_trace_stats.
 extern "C" int hs_trace(const uint8_t* blob, int mode, int64_t nray, const float* o, const float* d, uint8_t* hit,
                         uint8_t* front, int32_t* tri, float* loc, float* uv, int32_t* count, uint64_t* stats,

@@ -34,6 +34,7 @@ def lib():
         _LIB.hs_blob_bytes.restype = C.c_size_t
         _LIB.hs_blob_bytes.argtypes = [C.c_int64]
         _LIB.hs_build.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t]
+        _LIB.hs_build_sah.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t]
         _LIB.hs_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 10
         _LIB.hs_check_blob.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         _LIB.hs_blob_prims.argtypes = [C.c_void_p, C.c_void_p]
@@ -52,6 +53,17 @@ def build_blob(vertices, faces) -> np.ndarray:
     rc = lib().hs_build(_p(v), len(v), _p(f), len(f), _p(blob), blob.nbytes)
     if rc != 0:
         raise RuntimeError(f"hs_build failed: {rc}")
+    return blob
+
+
+def build_blob_sah(vertices, faces) -> np.ndarray:
+    """Experiment hook: BVH8 blob collapsed from a binned-SAH binary tree (see hs_build_sah)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32); f = np.ascontiguousarray(faces, dtype=np.int32)
+    nb = lib().hs_blob_bytes(len(f))
+    blob = np.zeros(nb, dtype=np.uint8)
+    rc = lib().hs_build_sah(_p(v), len(v), _p(f), len(f), _p(blob), nb)
+    if rc != 0:
+        raise RuntimeError(f"hs_build_sah failed: {rc}")
     return blob
 
 
