@@ -81,21 +81,30 @@ def broadcast_blob(blob: torch.Tensor | None, src: int = 0, group=None, device=N
 
 def gather_fixed(x: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
     """Concatenate per-rank tensors whose leading dimension is counts[rank] (ranks in order).
-    Uses a padded all_gather (every rank contributes max(counts) rows)."""
+    One padded all-gather into a flat buffer (every rank contributes max(counts) rows; the padding is
+    uninitialised and dropped), then one compaction copy - none when all ranks hold the same count."""
     world = dist.get_world_size(group)
     m = max(counts) if len(counts) else 0
     if m == 0:
         return x[:0]
-    pad = torch.zeros((m, *x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    if pad.dtype == torch.bool:
-        bufs = [torch.empty_like(pad, dtype=torch.uint8) for _ in range(world)]
-        dist.all_gather(bufs, pad.to(torch.uint8), group=group)
-        bufs = [b.to(torch.bool) for b in bufs]
+    as_bool = x.dtype == torch.bool
+    src = x.to(torch.uint8) if as_bool else x
+    if src.shape[0] == m:
+        pad = src.contiguous()
     else:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
+        pad = torch.empty((m, *src.shape[1:]), dtype=src.dtype, device=src.device)
+        pad[: src.shape[0]] = src
+    flat = torch.empty((world * m, *src.shape[1:]), dtype=src.dtype, device=src.device)
+    try:
+        dist.all_gather_into_tensor(flat, pad, group=group)
+    except (RuntimeError, NotImplementedError, AttributeError):      # backend without the flat variant
+        bufs = list(flat.split(m, dim=0))
         dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    if all(c == m for c in counts):
+        out = flat
+    else:
+        out = torch.cat([flat[r * m: r * m + c] for r, c in enumerate(counts)], dim=0)
+    return out.to(torch.bool) if as_bool else out
 
 
 def all_counts(n_local: int, device, group=None) -> List[int]:
