@@ -387,6 +387,23 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
     return hit, front, tri, loc, uv
 
 
+def intersects_closest_into(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, hit_ptr: int, front_ptr: int,
+                            tri_ptr: int, loc_ptr: int, uv_ptr: int) -> None:
+    """rt_trace_closest with caller-provided RAW output addresses (u8 hit, u8 front, i32 tri, f32 loc[3], f32 uv[2]
+    per ray, dense).  The addresses may be peer-GPU memory mapped into this process (NVLink P2P / symmetric
+    memory): the kernel then stores its results straight into another rank's tensors - the fused trace + gather
+    of triro.distributed.  Asynchronous on the current stream."""
+    tensor_input_check(origins, dirs)
+    blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
+    rd, _ = make_ray_desc(origins, dirs)
+    dev = origins.device
+    with torch.cuda.device(dev):
+        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), C.c_void_p(hit_ptr), C.c_void_p(front_ptr),
+                                             C.c_void_p(tri_ptr), C.c_void_p(loc_ptr), C.c_void_p(uv_ptr),
+                                             _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest")
+
+
 def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int, height: int, focal: float):
     """Closest hit of the pinhole camera rays of the reference's benchmark (gen_rays,
     test/performance_test.py:10-20) generated inside the kernel: no ray tensors are built or read.

@@ -116,6 +116,42 @@ def all_counts(n_local: int, device, group=None) -> List[int]:
     return [int(b.item()) for b in bufs]
 
 
+class PeerOutputs:
+    """Dense closest-hit outputs for `nray` rays in SYMMETRIC memory (torch.distributed._symmetric_memory): every
+    rank allocates the same buffer and learns the peer-mapped address of every other rank's copy, so a rank's
+    trace kernel can store its slice of the results directly into the root's buffer over NVLink - the gather is
+    fused into the kernel's own stores, there is no collective afterwards (only a barrier)."""
+
+    def __init__(self, nray: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.nray = int(nray)
+        a = lambda b: (b + 255) // 256 * 256
+        self.off_hit = 0
+        self.off_front = a(self.nray)
+        self.off_tri = self.off_front + a(self.nray)
+        self.off_loc = self.off_tri + a(4 * self.nray)
+        self.off_uv = self.off_loc + a(12 * self.nray)
+        self.bytes = self.off_uv + a(8 * self.nray)
+        self.buf = symm_mem.empty(self.bytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def addresses(self, rank: int, first_ray: int):
+        """Raw addresses of ray `first_ray`'s hit / front / tri / loc / uv slots in `rank`'s buffer."""
+        b = self.ptrs[rank]
+        return (b + self.off_hit + first_ray, b + self.off_front + first_ray, b + self.off_tri + 4 * first_ray,
+                b + self.off_loc + 12 * first_ray, b + self.off_uv + 8 * first_ray)
+
+    def local_views(self, batch):
+        n, u = self.nray, self.buf
+        return (u[self.off_hit:self.off_hit + n].view(torch.bool).reshape(batch),
+                u[self.off_front:self.off_front + n].view(torch.bool).reshape(batch),
+                u[self.off_tri:self.off_tri + 4 * n].view(torch.int32).reshape(batch),
+                u[self.off_loc:self.off_loc + 12 * n].view(torch.float32).reshape(*batch, 3),
+                u[self.off_uv:self.off_uv + 8 * n].view(torch.float32).reshape(*batch, 2))
+
+
 class ShardedRayMeshIntersector:
     """Wraps a per-rank intersector (anything with the RayMeshIntersector query methods).
 
@@ -204,6 +240,24 @@ class ShardedRayMeshIntersector:
         hc = all_counts(front.shape[0], front.device, self.group)
         return (hit_full, gather_fixed(front, hc, self.group), gather_fixed(ray_idx, hc, self.group),
                 gather_fixed(tri_idx, hc, self.group), gather_fixed(loc, hc, self.group), gather_fixed(uv, hc, self.group))
+
+    def intersects_closest_to_root(self, origins, directions, root: int = 0, outputs: "PeerOutputs | None" = None):
+        """Fused trace + gather: every rank traces its ray slice and its kernel stores the results straight into
+        `root`'s output tensors over NVLink (peer stores from inside k_trace; no all-gather).  Returns the dense
+        5-tuple of `intersects_closest` on `root` (views of `outputs`, valid until the next call that reuses it)
+        and None elsewhere.  Pass a `PeerOutputs` to reuse the symmetric allocation across calls."""
+        from triro.backend import ops as hops
+
+        batch = tuple(origins.shape[:-1])
+        n, lo, hi, o, d = self._slice(origins, directions)
+        if outputs is None or outputs.nray != n:
+            outputs = PeerOutputs(n, o.device, self.group)
+        if hi > lo:
+            hops.intersects_closest_into(self.local.as_wrapper, o, d, *outputs.addresses(root, lo))
+        torch.cuda.current_stream().synchronize()      # this rank's stores have left; then everybody's have
+        dist.barrier(group=self.group)
+        self._peer_outputs = outputs
+        return outputs.local_views(batch) if self.rank == root else None
 
     def intersects_location(self, origins, directions, gather: bool = True):
         n, lo, hi, o, d = self._slice(origins, directions)
