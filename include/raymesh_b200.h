@@ -158,6 +158,16 @@ int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* workspace,
                        uint8_t* front_out, int32_t* ray_idx_out, int32_t* tri_idx_out, float* loc_out,
                        float* uv_out, void* stream);
 
+/* Sharded variant (no counterpart in the single-GPU reference): the same scatter, but every ray index is
+ * written as ray_base + local index, as int32 (ray_idx_bytes 4) or int64 (8, for jobs of more than 2^31 rays), and the
+ * *_out pointers are taken as given - they may point into ANOTHER GPU's memory (NVLink peer mapping), already offset
+ * to this rank's first packed row, so that the ranks of a ray-sharded job pack their hits straight into one tensor
+ * on the root (triro/distributed.py). */
+int rt_compact_scatter_at(const uint8_t* hit, int64_t nray, const void* workspace,
+                          const uint8_t* front, const int32_t* tri_idx, const float* loc, const float* uv,
+                          int64_t ray_base, int ray_idx_bytes, uint8_t* front_out, void* ray_idx_out,
+                          int32_t* tri_idx_out, float* loc_out, float* uv_out, void* stream);
+
 /* ---- All hits: replaces intersectsLocation (ray.cpp:324-378; shaders.cu:196-246), i.e. the
  *      reference's count pass + clamp/cumsum (ray.cpp:333-342) + second traversal, in ONE traversal:
  *      step 1 traces once, storing up to max_hits (<= RT_MAX_HITS_LIMIT, reference: 8) hits per ray into
@@ -170,6 +180,11 @@ int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, in
 int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
                        const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
                        void* stream);
+
+/* Sharded variant of rt_allhits_scatter, see rt_compact_scatter_at. */
+int rt_allhits_scatter_at(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
+                          const void* workspace, int64_t ray_base, int ray_idx_bytes, float* loc_out,
+                          void* ray_idx_out, int32_t* tri_idx_out, void* stream);
 
 /* ---- contains_points core: replaces the two intersectsCount launches + ~15 torch kernels of
  *      ray_optix.py:236-267.  For each point traces +dir and -dir exhaustively and writes

@@ -1,7 +1,8 @@
 """GPU tier of the ray-sharding layer: torchrun with min(2, #GPUs) ranks over NCCL.  Checks that (a) the gathered
 N-rank result of ShardedRayMeshIntersector.intersects_closest and (b) the fused trace + gather
 (intersects_closest_to_root: k_trace stores straight into the root's symmetric-memory tensors over NVLink) are
-bit-identical to the oracle's MIRROR evaluator on the same rays."""
+bit-identical to the oracle's MIRROR evaluator on the same rays, and (c) that the fused variable-length routes
+(compacted closest hits, all hits: scatter kernels writing into the root's packed tensors) equal the NCCL gather."""
 import os
 import socket
 import subprocess
@@ -28,6 +29,21 @@ outs = PeerOutputs(o.numel() // 3, dev)
 peer = sh.intersects_closest_to_root(o, d, root=0, outputs=outs)
 peer2 = sh.intersects_closest_to_root(o, d, root=0, outputs=outs)      # buffer reuse
 assert (peer is None) == (rank != 0)
+# variable-length results packed on the root by the ranks' own scatter kernels
+comp_nccl = sh.intersects_closest(o, d, stream_compaction=True, gather=True)
+comp_peer = sh.intersects_closest_compact_to_root(o, d, root=0)
+comp_peer = sh.intersects_closest_compact_to_root(o, d, root=0, packed=sh.last_packed)       # buffer reuse
+o2, d2 = synth.random_rays(50_001, seed=5, device=dev, box=True)
+loc_nccl = sh.intersects_location(o2, d2, gather=True)
+loc_peer = sh.intersects_location_to_root(o2, d2, root=0)
+if rank == 0:
+    for a, b in zip(comp_nccl, comp_peer):
+        assert a.dtype == b.dtype and torch.equal(a, b), (a.shape, b.shape)
+    for a, b in zip(loc_nccl, loc_peer):
+        assert a.dtype == b.dtype and torch.equal(a, b), (a.shape, b.shape)
+    assert loc_peer[0].shape[0] > 1000 and comp_peer[1].shape[0] == int(comp_peer[0].sum())
+else:
+    assert comp_peer is None and loc_peer is None
 if rank == 0:
     from oracle import oracle
     om = oracle.OracleMesh(v, f)

@@ -64,6 +64,37 @@ for it in range(3):                      # the first pass pays NCCL's lazy all-g
     gather_times.append((time.perf_counter() - t0) * 1e3)
 gather_ms = min(gather_times[1:])
 assert g_ray.shape[0] == sum(counts) and bool((g_ray[1:] > g_ray[:-1]).all())      # ascending global ray order
+del g_ray, g_tri
+# whole call, full 6-tuple: (a) trace + compaction + NCCL all-gather of every array to every rank,
+# (b) fused: every rank's scatter kernel packs its hits straight into rank 0's tensors over NVLink
+def whole(fn, reps=3):
+    ts = []
+    for it in range(reps):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter(); res = fn(); torch.cuda.synchronize(); dist.barrier()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([min(ts[1:])], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), res
+t_nccl, res_nccl = whole(lambda: (lambda r6: [gather_fixed(r6[0], [rays_per_gpu] * world)] +
+                                  [gather_fixed(x if i != 1 else x.long() + base, counts) for i, x in enumerate(r6[1:])])(
+                                      r.intersects_closest(o, d, stream_compaction=True)))
+n_check = int(res_nccl[2].shape[0]); del res_nccl
+from triro.backend import ops as hops
+from triro.distributed import PeerPacked
+packed = PeerPacked(1 << (sum(counts) - 1).bit_length(), world * rays_per_gpu, dev)
+def fused():
+    hit, front, tri, loc, uv = hops.intersects_closest(r.as_wrapper, o, d)
+    ws, total = hops.compact_scan(hit)
+    cs = all_counts(total, dev)
+    rb = 8 if world * rays_per_gpu > 2**31 - 1 else 4
+    if total > 0:
+        hops.compact_scatter_at(hit, ws, front, tri, loc, uv, base, rb, *packed.addresses(0, sum(cs[:rank]), rb))
+    packed.peer_hit_mask(0, base, base + rays_per_gpu).copy_(hit.view(torch.uint8))
+    return sum(cs), rb
+t_fused, (h_fused, rb) = whole(fused)
+if rank == 0:
+    v = packed.local_views(h_fused, rb, (world * rays_per_gpu,))
+    assert h_fused == n_check and bool((v["ray"][1:] > v["ray"][:-1]).all()) and int(v["hit"].sum()) == h_fused
 assert int(hit.sum()) == ray_idx.shape[0] and bool((tri_idx >= 0).all())
 if rank == 0:
     h = r.as_wrapper.header
@@ -71,7 +102,7 @@ if rank == 0:
                 query="intersects_closest(stream_compaction=True)", ms=float(ms[0]),
                 mrays_s=world * rays_per_gpu / float(ms[0]) / 1e3, build_plus_broadcast_ms=build_bcast_ms,
                 broadcast_ms=bcast_ms, broadcast_gb_s=blob.numel() / bcast_ms / 1e6, blob_mb=blob.numel() / 1e6,
-                hits_total=sum(counts), gather_ray_tri_ms=gather_ms, gather_first_call_ms=gather_times[0], gathered_bytes=sum(counts) * 12)
+                hits_total=sum(counts), gather_ray_tri_ms=gather_ms, gather_first_call_ms=gather_times[0], whole_call_nccl_allgather_ms=t_nccl, whole_call_fused_to_root_ms=t_fused, gathered_bytes=sum(counts) * 12)
     print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(line, open(os.path.join(ROOT, "gpurun_out", f"config5_N{world}.json"), "w"), indent=1)

@@ -168,10 +168,14 @@ int scan_counts_i32(const int32_t* counts, int64_t n, void* workspace, size_t wo
 }
 
 // ------------------------------------------------------------------ scatter kernels (one CTA per tile)
+// RayIdx = int32_t (reference dtype) or int64_t (sharded jobs whose global ray numbering exceeds 2^31);
+// ray_base is added to the local ray index (0 for a single-GPU call).  The *_out pointers may be peer
+// memory: a rank of a sharded job scatters straight into the root's packed tensors at its global offset.
+template <class RayIdx>
 __global__ void __launch_bounds__(kScanThreads) k_compact_scatter(
     const uint8_t* __restrict__ hit, int64_t n, const long long* __restrict__ tile_prefix,
     const uint8_t* __restrict__ front, const int32_t* __restrict__ tri, const float* __restrict__ loc,
-    const float* __restrict__ uv, uint8_t* __restrict__ front_out, int32_t* __restrict__ ray_out,
+    const float* __restrict__ uv, int64_t ray_base, uint8_t* __restrict__ front_out, RayIdx* __restrict__ ray_out,
     int32_t* __restrict__ tri_out, float* __restrict__ loc_out, float* __restrict__ uv_out) {
     const int64_t tile = blockIdx.x;
     const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads) k_compact_scatter(
         if (v[j]) {
             const int64_t r = i0 + j;
             front_out[dst] = front[r];
-            ray_out[dst] = (int32_t)r;
+            ray_out[dst] = (RayIdx)(ray_base + r);
             tri_out[dst] = tri[r];
             loc_out[3 * dst] = loc[3 * r]; loc_out[3 * dst + 1] = loc[3 * r + 1]; loc_out[3 * dst + 2] = loc[3 * r + 2];
             uv_out[2 * dst] = uv[2 * r]; uv_out[2 * dst + 1] = uv[2 * r + 1];
@@ -197,10 +201,11 @@ __global__ void __launch_bounds__(kScanThreads) k_compact_scatter(
     }
 }
 
+template <class RayIdx>
 __global__ void __launch_bounds__(kScanThreads) k_allhits_scatter(
     int64_t n, int max_hits, const int32_t* __restrict__ count, const uint4* __restrict__ staging,
-    const long long* __restrict__ tile_prefix, float* __restrict__ loc_out, int32_t* __restrict__ ray_out,
-    int32_t* __restrict__ tri_out) {
+    const long long* __restrict__ tile_prefix, int64_t ray_base, float* __restrict__ loc_out,
+    RayIdx* __restrict__ ray_out, int32_t* __restrict__ tri_out) {
     const int64_t tile = blockIdx.x;
     const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kScanThreads) k_allhits_scatter(
         const int64_t r = i0 + j;
         for (int k = 0; k < v[j]; ++k) {
             const uint4 rec = staging[(size_t)r * max_hits + k];
-            ray_out[dst] = (int32_t)r;
+            ray_out[dst] = (RayIdx)(ray_base + r);
             tri_out[dst] = (int32_t)rec.x;
             loc_out[3 * dst] = __uint_as_float(rec.y);
             loc_out[3 * dst + 1] = __uint_as_float(rec.z);
@@ -243,17 +248,60 @@ extern "C" int rt_compact_scan(const uint8_t* hit, int64_t nray, void* workspace
                                  (cudaStream_t)stream);
 }
 
+static int compact_scatter(const char* fn, const uint8_t* hit, int64_t nray, const void* workspace, const uint8_t* front,
+                           const int32_t* tri_idx, const float* loc, const float* uv, int64_t ray_base, int ray_idx_bytes,
+                           uint8_t* front_out, void* ray_idx_out, int32_t* tri_idx_out, float* loc_out, float* uv_out,
+                           void* stream) {
+    RT_REQUIRE(nray >= 0, RT_ERR_INVALID, "%s: negative ray count", fn);
+    RT_REQUIRE(ray_idx_bytes == 4 || ray_idx_bytes == 8, RT_ERR_INVALID, "%s: ray_idx_bytes must be 4 or 8", fn);
+    if (nray == 0) return RT_OK;
+    RT_REQUIRE(hit && workspace && front && tri_idx && loc && uv, RT_ERR_INVALID, "%s: null input", fn);
+    // outputs may be null only when nothing was hit; the kernel then never dereferences them
+    ScanWorkspace w = carve_scan(const_cast<void*>(workspace), nray);
+    if (ray_idx_bytes == 4)
+        k_compact_scatter<int32_t><<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+            hit, nray, w.tile_prefix, front, tri_idx, loc, uv, ray_base, front_out, (int32_t*)ray_idx_out, tri_idx_out,
+            loc_out, uv_out);
+    else
+        k_compact_scatter<int64_t><<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+            hit, nray, w.tile_prefix, front, tri_idx, loc, uv, ray_base, front_out, (int64_t*)ray_idx_out, tri_idx_out,
+            loc_out, uv_out);
+    RT_CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
 extern "C" int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* workspace, const uint8_t* front,
                                   const int32_t* tri_idx, const float* loc, const float* uv, uint8_t* front_out,
                                   int32_t* ray_idx_out, int32_t* tri_idx_out, float* loc_out, float* uv_out,
                                   void* stream) {
-    RT_REQUIRE(nray >= 0, RT_ERR_INVALID, "rt_compact_scatter: negative ray count");
+    return compact_scatter("rt_compact_scatter", hit, nray, workspace, front, tri_idx, loc, uv, 0, 4, front_out,
+                           ray_idx_out, tri_idx_out, loc_out, uv_out, stream);
+}
+
+extern "C" int rt_compact_scatter_at(const uint8_t* hit, int64_t nray, const void* workspace, const uint8_t* front,
+                                     const int32_t* tri_idx, const float* loc, const float* uv, int64_t ray_base,
+                                     int ray_idx_bytes, uint8_t* front_out, void* ray_idx_out, int32_t* tri_idx_out,
+                                     float* loc_out, float* uv_out, void* stream) {
+    return compact_scatter("rt_compact_scatter_at", hit, nray, workspace, front, tri_idx, loc, uv, ray_base,
+                           ray_idx_bytes, front_out, ray_idx_out, tri_idx_out, loc_out, uv_out, stream);
+}
+
+static int allhits_scatter(const char* fn, int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
+                           const void* workspace, int64_t ray_base, int ray_idx_bytes, float* loc_out, void* ray_idx_out,
+                           int32_t* tri_idx_out, void* stream) {
+    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT, RT_ERR_INVALID, "%s: bad arguments", fn);
+    RT_REQUIRE(ray_idx_bytes == 4 || ray_idx_bytes == 8, RT_ERR_INVALID, "%s: ray_idx_bytes must be 4 or 8", fn);
     if (nray == 0) return RT_OK;
-    RT_REQUIRE(hit && workspace && front && tri_idx && loc && uv, RT_ERR_INVALID, "rt_compact_scatter: null input");
-    // outputs may be null only when nothing was hit; the kernel then never dereferences them
+    RT_REQUIRE(count_clamped && staging && workspace, RT_ERR_INVALID, "%s: null input", fn);
     ScanWorkspace w = carve_scan(const_cast<void*>(workspace), nray);
-    k_compact_scatter<<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
-        hit, nray, w.tile_prefix, front, tri_idx, loc, uv, front_out, ray_idx_out, tri_idx_out, loc_out, uv_out);
+    if (ray_idx_bytes == 4)
+        k_allhits_scatter<int32_t><<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+            nray, max_hits, count_clamped, reinterpret_cast<const uint4*>(staging), w.tile_prefix, ray_base, loc_out,
+            (int32_t*)ray_idx_out, tri_idx_out);
+    else
+        k_allhits_scatter<int64_t><<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
+            nray, max_hits, count_clamped, reinterpret_cast<const uint4*>(staging), w.tile_prefix, ray_base, loc_out,
+            (int64_t*)ray_idx_out, tri_idx_out);
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }
@@ -261,14 +309,13 @@ extern "C" int rt_compact_scatter(const uint8_t* hit, int64_t nray, const void* 
 extern "C" int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
                                   const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
                                   void* stream) {
-    RT_REQUIRE(nray >= 0 && max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT, RT_ERR_INVALID,
-               "rt_allhits_scatter: bad arguments");
-    if (nray == 0) return RT_OK;
-    RT_REQUIRE(count_clamped && staging && workspace, RT_ERR_INVALID, "rt_allhits_scatter: null input");
-    ScanWorkspace w = carve_scan(const_cast<void*>(workspace), nray);
-    k_allhits_scatter<<<(unsigned)w.tiles, kScanThreads, 0, (cudaStream_t)stream>>>(
-        nray, max_hits, count_clamped, reinterpret_cast<const uint4*>(staging), w.tile_prefix, loc_out, ray_idx_out,
-        tri_idx_out);
-    RT_CUDA_TRY(cudaGetLastError());
-    return RT_OK;
+    return allhits_scatter("rt_allhits_scatter", nray, max_hits, count_clamped, staging, workspace, 0, 4, loc_out,
+                           ray_idx_out, tri_idx_out, stream);
+}
+
+extern "C" int rt_allhits_scatter_at(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
+                                     const void* workspace, int64_t ray_base, int ray_idx_bytes, float* loc_out,
+                                     void* ray_idx_out, int32_t* tri_idx_out, void* stream) {
+    return allhits_scatter("rt_allhits_scatter_at", nray, max_hits, count_clamped, staging, workspace, ray_base,
+                           ray_idx_bytes, loc_out, ray_idx_out, tri_idx_out, stream);
 }

@@ -79,6 +79,8 @@ def _declare(lib):
         "rt_allhits_sizes": (ci, [i64, ci, psz, psz]),
         "rt_allhits_trace": (ci, [vp, prd, ci, vp, vp, vp, sz, vp, vp, vp]),
         "rt_allhits_scatter": (ci, [i64, ci, vp, vp, vp, vp, vp, vp, vp]),
+        "rt_allhits_scatter_at": (ci, [i64, ci, vp, vp, vp, i64, ci, vp, vp, vp, vp]),
+        "rt_compact_scatter_at": (ci, [vp, i64, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, vp]),
         "rt_contains_parity": (ci, [vp, prd, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
                                     vp, vp, vp]),
         "rt_trace_stats": (ci, [vp, prd, ci, vp, vp, vp]),
@@ -457,6 +459,62 @@ def compact_closest(hit, front, tri, loc, uv):
                                           _ptr(front_c), _ptr(ray_idx), _ptr(tri_c), _ptr(loc_c), _ptr(uv_c),
                                           _stream(dev)), "rt_compact_scatter")
     return front_c, ray_idx, tri_c, loc_c, uv_c
+
+
+def compact_scan(hit: torch.Tensor):
+    """First half of compact_closest: (workspace, number of hits) - the host reads the total."""
+    lib = get_module()
+    dev = hit.device
+    n = hit.numel()
+    with torch.cuda.device(dev):
+        ws_b = C.c_size_t()
+        _check(lib.rt_compact_sizes(n, C.byref(ws_b)), "rt_compact_sizes")
+        ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        _check(lib.rt_compact_scan(_ptr(hit), n, _ptr(ws), ws.numel(), _ptr(total), _stream(dev)), "rt_compact_scan")
+        return ws, int(total.item())
+
+
+def compact_scatter_at(hit, ws, front, tri, loc, uv, ray_base: int, ray_idx_bytes: int, front_ptr: int, ray_ptr: int,
+                       tri_ptr: int, loc_ptr: int, uv_ptr: int) -> None:
+    """Second half with RAW output addresses (possibly peer-GPU memory) already offset to this shard's first packed
+    row; ray indices are written as ray_base + local index (rt_compact_scatter_at)."""
+    dev = hit.device
+    with torch.cuda.device(dev):
+        _check(get_module().rt_compact_scatter_at(_ptr(hit), hit.numel(), _ptr(ws), _ptr(front), _ptr(tri), _ptr(loc),
+                                                  _ptr(uv), int(ray_base), int(ray_idx_bytes), C.c_void_p(front_ptr),
+                                                  C.c_void_p(ray_ptr), C.c_void_p(tri_ptr), C.c_void_p(loc_ptr),
+                                                  C.c_void_p(uv_ptr), _stream(dev)), "rt_compact_scatter_at")
+
+
+def allhits_trace(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = 8):
+    """First half of intersects_location: one traversal + scan -> (state for allhits_scatter_at, number of hits)."""
+    tensor_input_check(origins, dirs)
+    lib = get_module()
+    blob = _blob_of(accel_structure)
+    _apply_tmax(accel_structure)
+    rd, _ = make_ray_desc(origins, dirs)
+    dev = origins.device
+    n = rd.nray
+    with torch.cuda.device(dev):
+        st_b, ws_b = C.c_size_t(), C.c_size_t()
+        _check(lib.rt_allhits_sizes(n, max_hits, C.byref(st_b), C.byref(ws_b)), "rt_allhits_sizes")
+        staging = torch.empty(max(st_b.value, 16), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
+        counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        _check(lib.rt_allhits_trace(_ptr(blob), C.byref(rd), max_hits, _ptr(counts), _ptr(staging), _ptr(ws), ws.numel(),
+                                    _ptr(total), _ptr(_scratch(dev)), _stream(dev)), "rt_allhits_trace")
+        return (n, max_hits, counts, staging, ws), int(total.item())
+
+
+def allhits_scatter_at(state, ray_base: int, ray_idx_bytes: int, loc_ptr: int, ray_ptr: int, tri_ptr: int) -> None:
+    n, max_hits, counts, staging, ws = state
+    dev = counts.device
+    with torch.cuda.device(dev):
+        _check(get_module().rt_allhits_scatter_at(n, max_hits, _ptr(counts), _ptr(staging), _ptr(ws), int(ray_base),
+                                                  int(ray_idx_bytes), C.c_void_p(loc_ptr), C.c_void_p(ray_ptr),
+                                                  C.c_void_p(tri_ptr), _stream(dev)), "rt_allhits_scatter_at")
 
 
 def intersects_count(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:

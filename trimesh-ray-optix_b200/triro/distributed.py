@@ -152,6 +152,48 @@ class PeerOutputs:
                 u[self.off_uv:self.off_uv + 8 * n].view(torch.float32).reshape(*batch, 2))
 
 
+class PeerPacked:
+    """Packed (variable-length) results for up to `capacity` hits plus a dense hit mask for `nray` rays, in symmetric
+    memory: the ranks of a sharded job scatter their hits straight into the root's copy at their global row offset
+    (rt_compact_scatter_at / rt_allhits_scatter_at with peer addresses)."""
+
+    def __init__(self, capacity: int, nray: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.capacity, self.nray = int(capacity), int(nray)
+        a = lambda b: (b + 255) // 256 * 256
+        c = self.capacity
+        self.off_ray = 0
+        self.off_loc = a(8 * c)
+        self.off_uv = self.off_loc + a(12 * c)
+        self.off_tri = self.off_uv + a(8 * c)
+        self.off_front = self.off_tri + a(4 * c)
+        self.off_hit = self.off_front + a(c)
+        self.bytes = self.off_hit + a(self.nray)
+        self.buf = symm_mem.empty(self.bytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def addresses(self, rank: int, row: int, ray_bytes: int):
+        """(front, ray_idx, tri, loc, uv) addresses of packed row `row` in `rank`'s buffer."""
+        b = self.ptrs[rank]
+        return (b + self.off_front + row, b + self.off_ray + ray_bytes * row, b + self.off_tri + 4 * row,
+                b + self.off_loc + 12 * row, b + self.off_uv + 8 * row)
+
+    def peer_hit_mask(self, rank: int, lo: int, hi: int) -> torch.Tensor:
+        return self.handle.get_buffer(rank, (hi - lo,), torch.uint8, self.off_hit + lo)
+
+    def local_views(self, h: int, ray_bytes: int, batch):
+        u = self.buf
+        ray_dt = torch.int64 if ray_bytes == 8 else torch.int32
+        return dict(hit=u[self.off_hit:self.off_hit + self.nray].view(torch.bool).reshape(batch),
+                    front=u[self.off_front:self.off_front + h].view(torch.bool),
+                    ray=u[self.off_ray:self.off_ray + ray_bytes * h].view(ray_dt),
+                    tri=u[self.off_tri:self.off_tri + 4 * h].view(torch.int32),
+                    loc=u[self.off_loc:self.off_loc + 12 * h].view(torch.float32).reshape(h, 3),
+                    uv=u[self.off_uv:self.off_uv + 8 * h].view(torch.float32).reshape(h, 2))
+
+
 class ShardedRayMeshIntersector:
     """Wraps a per-rank intersector (anything with the RayMeshIntersector query methods).
 
@@ -258,6 +300,62 @@ class ShardedRayMeshIntersector:
         dist.barrier(group=self.group)
         self._peer_outputs = outputs
         return outputs.local_views(batch) if self.rank == root else None
+
+    def _packed_for(self, packed, hits: int, nray: int, device):
+        # every rank sees the same (hits, nray), so all take the same branch of this collective allocation
+        if packed is None or packed.capacity < hits or packed.nray != nray:
+            packed = PeerPacked(max(1024, 1 << max(hits - 1, 1).bit_length()), nray, device, self.group)
+        return packed
+
+    def intersects_closest_compact_to_root(self, origins, directions, root: int = 0, packed: "PeerPacked | None" = None):
+        """`intersects_closest(stream_compaction=True)` of the full batch, assembled on `root` without a collective on
+        the data path: every rank traces and scans its slice, the per-rank hit totals are exchanged (one int64 each),
+        and each rank's scatter kernel packs its hits straight into the root's tensors at its global row offset, with
+        ray indices in the global numbering (int64 when the batch exceeds 2^31 rays).  Returns the 6-tuple on `root`
+        (views of `packed`, see `last_packed`), None elsewhere."""
+        from triro.backend import ops as hops
+
+        batch = tuple(origins.shape[:-1])
+        n, lo, hi, o, d = self._slice(origins, directions)
+        hit, front, tri, loc, uv = hops.intersects_closest(self.local.as_wrapper, o, d)
+        ws, total = hops.compact_scan(hit)
+        counts = all_counts(total, hit.device, self.group)
+        hits, row0 = sum(counts), sum(counts[: self.rank])
+        packed = self._packed_for(packed, hits, n, hit.device)
+        rb = 8 if n > 2**31 - 1 else 4
+        if total > 0:
+            hops.compact_scatter_at(hit, ws, front, tri, loc, uv, lo, rb, *packed.addresses(root, row0, rb))
+        if hi > lo:
+            packed.peer_hit_mask(root, lo, hi).copy_(hit.reshape(-1).view(torch.uint8))
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+        self.last_packed = packed
+        if self.rank != root:
+            return None
+        v = packed.local_views(hits, rb, batch)
+        return v["hit"], v["front"], v["ray"], v["tri"], v["loc"], v["uv"]
+
+    def intersects_location_to_root(self, origins, directions, root: int = 0, packed: "PeerPacked | None" = None):
+        """`intersects_location` (all hits, <= max_hits per ray) of the full batch packed on `root` the same way:
+        (loc[h,3], ray_idx[h], tri_idx[h]) on `root`, None elsewhere."""
+        from triro.backend import ops as hops
+
+        n, lo, hi, o, d = self._slice(origins, directions)
+        state, total = hops.allhits_trace(self.local.as_wrapper, o, d, getattr(self.local, "max_hits", 8))
+        counts = all_counts(total, o.device, self.group)
+        hits, row0 = sum(counts), sum(counts[: self.rank])
+        packed = self._packed_for(packed, hits, n, o.device)
+        rb = 8 if n > 2**31 - 1 else 4
+        if total > 0:
+            _, ray_p, tri_p, loc_p, _ = packed.addresses(root, row0, rb)
+            hops.allhits_scatter_at(state, lo, rb, loc_p, ray_p, tri_p)
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+        self.last_packed = packed
+        if self.rank != root:
+            return None
+        v = packed.local_views(hits, rb, (n,))
+        return v["loc"], v["ray"], v["tri"]
 
     def intersects_location(self, origins, directions, gather: bool = True):
         n, lo, hi, o, d = self._slice(origins, directions)
