@@ -33,6 +33,12 @@ assert (peer is None) == (rank != 0)
 comp_nccl = sh.intersects_closest(o, d, stream_compaction=True, gather=True)
 comp_peer = sh.intersects_closest_compact_to_root(o, d, root=0)
 comp_peer = sh.intersects_closest_compact_to_root(o, d, root=0, packed=sh.last_packed)       # buffer reuse
+if rank == 0:
+    comp_peer = tuple(x.clone() for x in comp_peer)
+comp_peer_k = sh.intersects_closest_compact_to_root(o, d, root=0, packed=sh.last_packed, scatter_to_peer=True)
+if rank == 0:
+    for a, b in zip(comp_peer, comp_peer_k):
+        assert torch.equal(a, b)
 o2, d2 = synth.random_rays(50_001, seed=5, device=dev, box=True)
 loc_nccl = sh.intersects_location(o2, d2, gather=True)
 loc_peer = sh.intersects_location_to_root(o2, d2, root=0)

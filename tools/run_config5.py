@@ -82,16 +82,27 @@ n_check = int(res_nccl[2].shape[0]); del res_nccl
 from triro.backend import ops as hops
 from triro.distributed import PeerPacked
 packed = PeerPacked(1 << (sum(counts) - 1).bit_length(), world * rays_per_gpu, dev)
-def fused():
+def fused(scatter_to_peer):
     hit, front, tri, loc, uv = hops.intersects_closest(r.as_wrapper, o, d)
     ws, total = hops.compact_scan(hit)
-    cs = all_counts(total, dev)
     rb = 8 if world * rays_per_gpu > 2**31 - 1 else 4
-    if total > 0:
-        hops.compact_scatter_at(hit, ws, front, tri, loc, uv, base, rb, *packed.addresses(0, sum(cs[:rank]), rb))
+    if not scatter_to_peer:       # pack locally, then bulk peer-to-peer copies into the root's tensors
+        mine = dict(front=torch.empty(total, dtype=torch.uint8, device=dev), ray=torch.empty(total, dtype=torch.int64 if rb == 8 else torch.int32, device=dev),
+                    tri=torch.empty(total, dtype=torch.int32, device=dev), loc=torch.empty(3 * total, dtype=torch.float32, device=dev),
+                    uv=torch.empty(2 * total, dtype=torch.float32, device=dev))
+        hops.compact_scatter_at(hit, ws, front, tri, loc, uv, base, rb, mine["front"].data_ptr(), mine["ray"].data_ptr(),
+                                mine["tri"].data_ptr(), mine["loc"].data_ptr(), mine["uv"].data_ptr())
+    cs = all_counts(total, dev)
+    row0 = sum(cs[:rank])
+    if scatter_to_peer:
+        hops.compact_scatter_at(hit, ws, front, tri, loc, uv, base, rb, *packed.addresses(0, row0, rb))
+    else:
+        for name, t in mine.items():
+            packed.peer_rows(0, name, row0, total, rb).copy_(t)
     packed.peer_hit_mask(0, base, base + rays_per_gpu).copy_(hit.view(torch.uint8))
     return sum(cs), rb
-t_fused, (h_fused, rb) = whole(fused)
+t_fused_scatter, _ = whole(lambda: fused(True))
+t_fused, (h_fused, rb) = whole(lambda: fused(False))
 if rank == 0:
     v = packed.local_views(h_fused, rb, (world * rays_per_gpu,))
     assert h_fused == n_check and bool((v["ray"][1:] > v["ray"][:-1]).all()) and int(v["hit"].sum()) == h_fused
@@ -102,7 +113,7 @@ if rank == 0:
                 query="intersects_closest(stream_compaction=True)", ms=float(ms[0]),
                 mrays_s=world * rays_per_gpu / float(ms[0]) / 1e3, build_plus_broadcast_ms=build_bcast_ms,
                 broadcast_ms=bcast_ms, broadcast_gb_s=blob.numel() / bcast_ms / 1e6, blob_mb=blob.numel() / 1e6,
-                hits_total=sum(counts), gather_ray_tri_ms=gather_ms, gather_first_call_ms=gather_times[0], whole_call_nccl_allgather_ms=t_nccl, whole_call_fused_to_root_ms=t_fused, gathered_bytes=sum(counts) * 12)
+                hits_total=sum(counts), gather_ray_tri_ms=gather_ms, gather_first_call_ms=gather_times[0], whole_call_nccl_allgather_ms=t_nccl, whole_call_peer_copies_to_root_ms=t_fused, whole_call_peer_scatter_to_root_ms=t_fused_scatter, gathered_bytes=sum(counts) * 12)
     print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(line, open(os.path.join(ROOT, "gpurun_out", f"config5_N{world}.json"), "w"), indent=1)

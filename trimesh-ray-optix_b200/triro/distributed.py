@@ -183,6 +183,14 @@ class PeerPacked:
     def peer_hit_mask(self, rank: int, lo: int, hi: int) -> torch.Tensor:
         return self.handle.get_buffer(rank, (hi - lo,), torch.uint8, self.off_hit + lo)
 
+    def peer_rows(self, rank: int, name: str, row: int, rows: int, ray_bytes: int = 4) -> torch.Tensor:
+        """Tensor aliasing rows [row, row + rows) of section `name` in `rank`'s buffer (peer-mapped memory)."""
+        off, dt, width = {"front": (self.off_front, torch.uint8, 1), "tri": (self.off_tri, torch.int32, 1),
+                          "ray": (self.off_ray, torch.int64 if ray_bytes == 8 else torch.int32, 1),
+                          "loc": (self.off_loc, torch.float32, 3), "uv": (self.off_uv, torch.float32, 2)}[name]
+        item = torch.empty(0, dtype=dt).element_size()
+        return self.handle.get_buffer(rank, (rows * width,), dt, off // item + row * width)
+
     def local_views(self, h: int, ray_bytes: int, batch):
         u = self.buf
         ray_dt = torch.int64 if ray_bytes == 8 else torch.int32
@@ -307,24 +315,42 @@ class ShardedRayMeshIntersector:
             packed = PeerPacked(max(1024, 1 << max(hits - 1, 1).bit_length()), nray, device, self.group)
         return packed
 
-    def intersects_closest_compact_to_root(self, origins, directions, root: int = 0, packed: "PeerPacked | None" = None):
-        """`intersects_closest(stream_compaction=True)` of the full batch, assembled on `root` without a collective on
-        the data path: every rank traces and scans its slice, the per-rank hit totals are exchanged (one int64 each),
-        and each rank's scatter kernel packs its hits straight into the root's tensors at its global row offset, with
-        ray indices in the global numbering (int64 when the batch exceeds 2^31 rays).  Returns the 6-tuple on `root`
-        (views of `packed`, see `last_packed`), None elsewhere."""
+    def intersects_closest_compact_to_root(self, origins, directions, root: int = 0, packed: "PeerPacked | None" = None,
+                                           scatter_to_peer: bool = False):
+        """`intersects_closest(stream_compaction=True)` of the full batch, assembled on `root` without an NCCL
+        collective on the data path: every rank traces, scans and packs its slice (ray indices in the global
+        numbering, int64 when the batch exceeds 2^31 rays), the per-rank hit totals are exchanged (one int64 each),
+        and each rank copies its packed arrays into the root's tensors at its global row offset with plain
+        peer-to-peer copies over NVLink - no padding, no concatenation pass.  `scatter_to_peer=True` instead lets the
+        scatter kernel store into the root's memory directly (measured slower: small strided NVLink stores).
+        Returns the 6-tuple on `root` (views of `packed`, kept in `last_packed`), None elsewhere."""
         from triro.backend import ops as hops
 
         batch = tuple(origins.shape[:-1])
         n, lo, hi, o, d = self._slice(origins, directions)
+        dev = o.device
         hit, front, tri, loc, uv = hops.intersects_closest(self.local.as_wrapper, o, d)
         ws, total = hops.compact_scan(hit)
-        counts = all_counts(total, hit.device, self.group)
-        hits, row0 = sum(counts), sum(counts[: self.rank])
-        packed = self._packed_for(packed, hits, n, hit.device)
         rb = 8 if n > 2**31 - 1 else 4
+        mine = None
+        if not scatter_to_peer:
+            mine = dict(front=torch.empty(total, dtype=torch.uint8, device=dev),
+                        ray=torch.empty(total, dtype=torch.int64 if rb == 8 else torch.int32, device=dev),
+                        tri=torch.empty(total, dtype=torch.int32, device=dev),
+                        loc=torch.empty(3 * total, dtype=torch.float32, device=dev),
+                        uv=torch.empty(2 * total, dtype=torch.float32, device=dev))
+            if total > 0:
+                hops.compact_scatter_at(hit, ws, front, tri, loc, uv, lo, rb, mine["front"].data_ptr(), mine["ray"].data_ptr(),
+                                        mine["tri"].data_ptr(), mine["loc"].data_ptr(), mine["uv"].data_ptr())
+        counts = all_counts(total, dev, self.group)
+        hits, row0 = sum(counts), sum(counts[: self.rank])
+        packed = self._packed_for(packed, hits, n, dev)
         if total > 0:
-            hops.compact_scatter_at(hit, ws, front, tri, loc, uv, lo, rb, *packed.addresses(root, row0, rb))
+            if scatter_to_peer:
+                hops.compact_scatter_at(hit, ws, front, tri, loc, uv, lo, rb, *packed.addresses(root, row0, rb))
+            else:
+                for name, t in mine.items():
+                    packed.peer_rows(root, name, row0, total, rb).copy_(t)
         if hi > lo:
             packed.peer_hit_mask(root, lo, hi).copy_(hit.reshape(-1).view(torch.uint8))
         torch.cuda.current_stream().synchronize()
@@ -341,14 +367,20 @@ class ShardedRayMeshIntersector:
         from triro.backend import ops as hops
 
         n, lo, hi, o, d = self._slice(origins, directions)
+        dev = o.device
         state, total = hops.allhits_trace(self.local.as_wrapper, o, d, getattr(self.local, "max_hits", 8))
-        counts = all_counts(total, o.device, self.group)
-        hits, row0 = sum(counts), sum(counts[: self.rank])
-        packed = self._packed_for(packed, hits, n, o.device)
         rb = 8 if n > 2**31 - 1 else 4
+        mine = dict(loc=torch.empty(3 * total, dtype=torch.float32, device=dev),
+                    ray=torch.empty(total, dtype=torch.int64 if rb == 8 else torch.int32, device=dev),
+                    tri=torch.empty(total, dtype=torch.int32, device=dev))
         if total > 0:
-            _, ray_p, tri_p, loc_p, _ = packed.addresses(root, row0, rb)
-            hops.allhits_scatter_at(state, lo, rb, loc_p, ray_p, tri_p)
+            hops.allhits_scatter_at(state, lo, rb, mine["loc"].data_ptr(), mine["ray"].data_ptr(), mine["tri"].data_ptr())
+        counts = all_counts(total, dev, self.group)
+        hits, row0 = sum(counts), sum(counts[: self.rank])
+        packed = self._packed_for(packed, hits, n, dev)
+        if total > 0:
+            for name, t in mine.items():
+                packed.peer_rows(root, name, row0, total, rb).copy_(t)
         torch.cuda.current_stream().synchronize()
         dist.barrier(group=self.group)
         self.last_packed = packed
