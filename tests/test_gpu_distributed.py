@@ -26,8 +26,13 @@ sh = ShardedRayMeshIntersector.build(torch.from_numpy(v), torch.from_numpy(f), s
 o, d = synth.readme_rays(301, device=dev)          # odd size: ragged slices
 full = sh.intersects_closest(o, d, gather=True)
 outs = PeerOutputs(o.numel() // 3, dev)
-peer = sh.intersects_closest_to_root(o, d, root=0, outputs=outs)
+peer = sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=True)
 peer2 = sh.intersects_closest_to_root(o, d, root=0, outputs=outs)      # buffer reuse
+if rank == 0:
+    peer2 = tuple(x.clone() for x in peer2)
+peer3 = sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=False)     # peer-to-peer copies instead
+if rank == 0:
+    assert all(torch.equal(a, b) for a, b in zip(peer2, peer3))
 assert (peer is None) == (rank != 0)
 # variable-length results packed on the root by the ranks' own scatter kernels
 comp_nccl = sh.intersects_closest(o, d, stream_compaction=True, gather=True)

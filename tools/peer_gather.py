@@ -30,13 +30,18 @@ def timed(fn, reps=8):
 t_local, res_local = timed(lambda: sh.intersects_closest(o, d, gather=False))
 t_gather, res_gather = timed(lambda: sh.intersects_closest(o, d, gather=True))
 outs = PeerOutputs(n, dev)
-t_peer, res_peer = timed(lambda: sh.intersects_closest_to_root(o, d, root=0, outputs=outs))
+t_peer, res_peer = timed(lambda: sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=True))
+t_copy, res_copy = timed(lambda: sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=False))
 ok = True
+if rank == 0:          # res_peer and res_copy alias the same symmetric buffer: the copy route ran last
+    for a, b in zip(res_gather, res_copy):
+        ok = ok and bool(torch.equal(a, b))
+res_peer = sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=True)      # collective: every rank calls it
 if rank == 0:
     for a, b in zip(res_gather, res_peer):
         ok = ok and bool(torch.equal(a, b))
     line = dict(n_gpus=world, rays=n, trace_only_sharded_ms=t_local, trace_plus_nccl_allgather_ms=t_gather,
-                trace_with_peer_stores_to_root_ms=t_peer, identical=ok,
+                trace_with_peer_stores_to_root_ms=t_peer, trace_then_peer_copies_to_root_ms=t_copy, identical=ok,
                 mrays_s_peer=n / t_peer / 1e3, mrays_s_allgather=n / t_gather / 1e3)
     print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
