@@ -68,3 +68,22 @@ def test_slice_rays_handles_strided_and_broadcast_batches():
     o = torch.tensor([1.0, 2.0, 3.0]).broadcast_to(d.shape)
     so, sd = tdist.slice_rays(o, d, 5, 17)
     assert so.shape == (12, 3) and torch.equal(sd, d.reshape(-1, 3)[5:17]) and torch.all(so == torch.tensor([1.0, 2.0, 3.0]))
+
+
+def test_symmetric_buffer_layouts_are_aligned_and_disjoint():
+    """Section offsets of the peer-memory result buffers (triro/distributed.py): 256-byte aligned, large enough,
+    non-overlapping - the kernels and peer copies of the sharded gather write through raw addresses into them."""
+    from triro.distributed import dense_layout, packed_layout
+
+    for n in (0, 1, 255, 256, 257, 90_601, 8_294_400, 3_000_000_000):
+        lay = dense_layout(n)
+        need = dict(hit=n, front=n, tri=4 * n, loc=12 * n, uv=8 * n)
+        order = sorted(need, key=lambda k: lay[k])
+        for a, b in zip(order, order[1:] + ["bytes"]):
+            assert lay[a] % 256 == 0 and lay[a] + need[a] <= lay[b]
+    for cap, n in ((1024, 10), (1 << 20, 90_601), (1 << 28, 1_000_000_000)):
+        lay = packed_layout(cap, n)
+        need = dict(ray=8 * cap, loc=12 * cap, uv=8 * cap, tri=4 * cap, front=cap, hit=n)
+        order = sorted(need, key=lambda k: lay[k])
+        for a, b in zip(order, order[1:] + ["bytes"]):
+            assert lay[a] % 256 == 0 and lay[a] + need[a] <= lay[b]

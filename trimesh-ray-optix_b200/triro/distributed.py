@@ -116,6 +116,33 @@ def all_counts(n_local: int, device, group=None) -> List[int]:
     return [int(b.item()) for b in bufs]
 
 
+def _align256(b: int) -> int:
+    return (b + 255) // 256 * 256
+
+
+def dense_layout(nray: int) -> dict:
+    """Byte offsets of the dense closest-hit sections for `nray` rays (each 256-byte aligned): hit u8, front u8,
+    tri i32, loc f32x3, uv f32x2; 'bytes' = total."""
+    off, out = 0, {}
+    for name, per_ray in (("hit", 1), ("front", 1), ("tri", 4), ("loc", 12), ("uv", 8)):
+        out[name] = off
+        off += _align256(per_ray * nray)
+    out["bytes"] = off
+    return out
+
+
+def packed_layout(capacity: int, nray: int) -> dict:
+    """Byte offsets of the packed-result sections for up to `capacity` hits (ray index reserved at 8 bytes) plus
+    the dense hit mask of `nray` rays."""
+    off, out = 0, {}
+    for name, size in (("ray", 8 * capacity), ("loc", 12 * capacity), ("uv", 8 * capacity), ("tri", 4 * capacity),
+                       ("front", capacity), ("hit", nray)):
+        out[name] = off
+        off += _align256(size)
+    out["bytes"] = off
+    return out
+
+
 class PeerOutputs:
     """Dense closest-hit outputs for `nray` rays in SYMMETRIC memory (torch.distributed._symmetric_memory): every
     rank allocates the same buffer and learns the peer-mapped address of every other rank's copy, so a rank's
@@ -126,13 +153,9 @@ class PeerOutputs:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.nray = int(nray)
-        a = lambda b: (b + 255) // 256 * 256
-        self.off_hit = 0
-        self.off_front = a(self.nray)
-        self.off_tri = self.off_front + a(self.nray)
-        self.off_loc = self.off_tri + a(4 * self.nray)
-        self.off_uv = self.off_loc + a(12 * self.nray)
-        self.bytes = self.off_uv + a(8 * self.nray)
+        lay = dense_layout(self.nray)
+        self.off_hit, self.off_front, self.off_tri = lay["hit"], lay["front"], lay["tri"]
+        self.off_loc, self.off_uv, self.bytes = lay["loc"], lay["uv"], lay["bytes"]
         self.buf = symm_mem.empty(self.bytes, dtype=torch.uint8, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
@@ -168,15 +191,9 @@ class PeerPacked:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.capacity, self.nray = int(capacity), int(nray)
-        a = lambda b: (b + 255) // 256 * 256
-        c = self.capacity
-        self.off_ray = 0
-        self.off_loc = a(8 * c)
-        self.off_uv = self.off_loc + a(12 * c)
-        self.off_tri = self.off_uv + a(8 * c)
-        self.off_front = self.off_tri + a(4 * c)
-        self.off_hit = self.off_front + a(c)
-        self.bytes = self.off_hit + a(self.nray)
+        lay = packed_layout(self.capacity, self.nray)
+        self.off_ray, self.off_loc, self.off_uv, self.off_tri = lay["ray"], lay["loc"], lay["uv"], lay["tri"]
+        self.off_front, self.off_hit, self.bytes = lay["front"], lay["hit"], lay["bytes"]
         self.buf = symm_mem.empty(self.bytes, dtype=torch.uint8, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
