@@ -9,6 +9,7 @@
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -mfma -shared -fPIC hostsim.cpp -o libhostsim.so
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -20,12 +21,18 @@ using namespace rt;
 
 namespace {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// same rule as rt_api.h: kLeafTrisDefault, or TRIRO_LEAF_TRIS=1..3 (read at every call here, so tests can switch it)
+int leaf_setting() {
+    const char* e = getenv("TRIRO_LEAF_TRIS");
+    const int x = e ? atoi(e) : kLeafTrisDefault;
+    return x < 1 ? 1 : (x > kLeafMaxTris ? kLeafMaxTris : x);
+}
 struct Layout { size_t tris_offset, nodes_offset, parents_offset, total; uint32_t node_cap; };
 Layout layout(int64_t n) {
     Layout l;
     l.tris_offset = RT_BLOB_HEADER_BYTES;
     l.nodes_offset = align_up(l.tris_offset + (size_t)n * 48u, 256);
-    l.node_cap = (uint32_t)(n / 3 + 2);
+    l.node_cap = wide_node_cap(n, leaf_setting());
     l.parents_offset = align_up(l.nodes_offset + (size_t)l.node_cap * 80u, 256);
     l.total = l.parents_offset + align_up((size_t)l.node_cap * 4u, 256);
     return l;
@@ -108,7 +115,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     std::vector<uint32_t> wide_src(lay.node_cap, 0);
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
-    t.box = box.data(); t.sorted_prim = vals.data();
+    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting();
     CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
@@ -224,7 +231,7 @@ extern "C" int hs_build_sah(const float* verts, int64_t nv, const int32_t* faces
     std::vector<uint32_t> wide_src(lay.node_cap, 0);
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
-    t.box = box.data(); t.sorted_prim = vals.data();
+    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting();
     CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);

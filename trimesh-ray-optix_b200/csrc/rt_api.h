@@ -5,7 +5,9 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/raymesh_b200.h"
+#include "rt_core.cuh"
 
 namespace rt {
 
@@ -32,6 +34,17 @@ int device_info(DeviceInfo* out);
 
 inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Triangles per leaf slot used by the builder: kLeafTrisDefault, or TRIRO_LEAF_TRIS=1..3 (read once per process;
+// sizes, build and refit of one process always agree).
+inline int leaf_tris_setting() {
+    static const int v = [] {
+        const char* e = getenv("TRIRO_LEAF_TRIS");
+        const int x = e ? atoi(e) : kLeafTrisDefault;
+        return x < 1 ? 1 : (x > kLeafMaxTris ? kLeafMaxTris : x);
+    }();
+    return v;
+}
+
 // Blob geometry derived from the triangle count alone (host side, no device read needed).
 struct BlobLayout {
     size_t tris_offset, nodes_offset, parents_offset, total_bytes;
@@ -41,8 +54,7 @@ inline BlobLayout blob_layout(int64_t n_faces) {
     BlobLayout l;
     l.tris_offset = RT_BLOB_HEADER_BYTES;
     l.nodes_offset = align_up_sz(l.tris_offset + (size_t)(n_faces > 0 ? n_faces : 0) * 48u, 256);
-    // wide nodes <= n/3 + 2 (every bottom node holds > 3 triangles, every upper node has 8 children)
-    l.node_cap = (uint32_t)((n_faces > 0 ? n_faces : 0) / 3 + 2);
+    l.node_cap = wide_node_cap(n_faces, leaf_tris_setting());
     l.parents_offset = align_up_sz(l.nodes_offset + (size_t)l.node_cap * 80u, 256);
     l.total_bytes = l.parents_offset + align_up_sz((size_t)l.node_cap * 4u, 256);
     return l;

@@ -368,7 +368,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
 
         BinaryTree t;
         t.n = n; t.left = w.left; t.right = w.right; t.first = w.first; t.last = w.last; t.box = w.box;
-        t.sorted_prim = w.vals;
+        t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting();
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
         o.parent = reinterpret_cast<uint32_t*>(blob8 + lay.parents_offset);

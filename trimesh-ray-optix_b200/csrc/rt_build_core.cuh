@@ -133,6 +133,7 @@ struct BinaryTree {
     const uint32_t* last;         // [n-1]
     const BBox* box;              // [2n-1] internal boxes then leaf boxes
     const uint32_t* sorted_prim;  // [n] triangle id at each sorted position
+    int leaf_max;                 // subtrees of <= leaf_max triangles become one leaf slot (1..kLeafMaxTris)
 };
 
 RT_HD uint32_t bt_count(const BinaryTree& t, uint32_t ref) {
@@ -192,8 +193,8 @@ struct CollapseOut {
 
 // Builds wide node `w` from the binary subtree `wide_src[w]`.  Greedy surface-area expansion:
 // starting from the two children, repeatedly replace the child with the largest box that is
-// still expandable (an inner node covering more than kLeafMaxTris triangles) by its own two
-// children until there are 8 children.  Subtrees with <= kLeafMaxTris triangles become leaf
+// still expandable (an inner node covering more than leaf_max triangles) by its own two
+// children until there are 8 children.  Subtrees with <= leaf_max triangles become leaf
 // slots (their triangles are contiguous in Morton order).
 // Quantisation of the child boxes of one wide node: frame (p, 2^e) from the node box, 8-bit planes
 // rounded outwards and verified in binary64 against the exact decode p + q * 2^e.  Shared by the
@@ -304,7 +305,7 @@ RT_HD BBox refit_node(uint8_t* nodes, const uint8_t* tris, uint32_t w, const BBo
 }
 
 RT_HD bool bt_expandable(const BinaryTree& t, uint32_t ref) {
-    return ref < (uint32_t)(t.n - 1) && bt_count(t, ref) > (uint32_t)kLeafMaxTris;
+    return ref < (uint32_t)(t.n - 1) && bt_count(t, ref) > (uint32_t)t.leaf_max;
 }
 RT_HD float box_area(const BBox& b) {
     const float a = bbox_half_area(b);
@@ -327,8 +328,8 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     int k = 0;
     const uint32_t src = load_cg_u32(&o.wide_src[w]);
     const BBox nb = t.box[src];
-    if (t.n <= (int64_t)kLeafMaxTris) {
-        // whole mesh fits one leaf slot (n = 1..3): root with a single leaf child
+    if (t.n <= (int64_t)t.leaf_max) {
+        // whole mesh fits one leaf slot: root with a single leaf child
         ref[0] = src; area[0] = 0.0f; inner[0] = false; cb[0] = nb; k = 1;
     } else {
         // the box record of an inner binary node carries its two child references in the pad words

@@ -65,8 +65,15 @@ RT_HD float as_float(uint32_t u) { union { uint32_t u; float f; } c; c.u = u; re
 // Blob = [header 256 B][triangle records 48 B each][BVH8 nodes 80 B each].
 // All sections are 16-byte aligned so every fetch is a 128-bit ld.global.nc.
 
-constexpr int kLeafMaxTris = 3;    // triangles per leaf slot (unary-coded in 3 bits)
+constexpr int kLeafMaxTris = 3;    // most triangles a leaf slot can hold (unary-coded in 3 bits)
+constexpr int kLeafTrisDefault = 2; // what the builder puts into one leaf slot (TRIRO_LEAF_TRIS=1..3 overrides, for experiments)
 constexpr int kNodeMaxTris = 24;   // 8 slots x 3
+// Upper bound of the number of wide nodes for n triangles.  A bottom node holds more than leaf_max triangles
+// (else it would have been a leaf slot of its parent), upper levels add at most 1/7 on top.
+RT_HD uint32_t wide_node_cap(int64_t n, int leaf_max) {
+    const int64_t m = n > 0 ? n : 0;
+    return (uint32_t)(leaf_max >= 3 ? m / 3 + 2 : (leaf_max == 2 ? (2 * m) / 5 + 2 : (5 * m) / 8 + 2));
+}
 constexpr int kMaxDepth = 60;      // wide-tree levels the traversal stack can hold
 
 struct alignas(16) TriRecord {     // 48 B: three 128-bit loads
