@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 /* reference: LaunchParams.h:8-9 */
 #define RT_MAX_ANYHIT_SIZE 8
@@ -88,17 +88,53 @@ typedef struct rt_blob_header {
     uint32_t reserved[40];
 } rt_blob_header;
 
-/* Size of the scratch buffer every trace call needs (zeroed by the call itself). */
+/* Size of the scratch buffer every trace call needs (zeroed by the call itself unless
+ * RT_OPT_SCRATCH_ZEROED is set, see rt_trace_opts). */
 #define RT_TRACE_SCRATCH_BYTES 256
+
+/*
+ * Per-call options of every trace entry point (NULL = all defaults).  Replaces what the reference
+ * hard-codes: tmin = 0 / tmax = 1e7 on every optixTrace (shaders.cu:86,112,163,191,238).  There is no
+ * per-thread or per-process state behind the trace calls: everything a launch depends on is in its
+ * arguments.
+ *   tmax        far end of the open ray interval (0, tmax); <= 0 selects RT_TMAX_DEFAULT.
+ *   ray_first / ray_count
+ *               trace only rays [ray_first, ray_first + ray_count) of the descriptor's flattened
+ *               (row-major) index space; ray_count <= 0 = up to the end, so a zero-initialised struct
+ *               means the whole batch (a caller with an empty window simply does not call).  Outputs are indexed by
+ *               (ray - ray_first), i.e. the output pointers belong to the window.  Lets a caller
+ *               chunk or shard an arbitrarily strided batch without copying it.
+ *   schedule    RT_SCHED_AUTO picks by ray coherence (one shared origin = coherent); the others
+ *               force a traversal schedule (all give bit-identical results).
+ *   refill_threshold, tri_threshold, grid_div
+ *               scheduling knobs for experiments, 0 = default.
+ *   flags       RT_OPT_SCRATCH_ZEROED: the caller guarantees that `scratch` is all zero on entry
+ *               (stream-ordered); the kernel then restores it to zero before it exits, so a launch
+ *               is exactly one kernel and the same scratch can be reused by the next call on the
+ *               same stream without a memset.
+ */
+#define RT_SCHED_AUTO 0
+#define RT_SCHED_DIRECT 1       /* triangles tested inside the node step, per lane (round-1 coherent schedule) */
+#define RT_SCHED_QUEUED 2       /* per-lane triangle queues (round-1 incoherent schedule) */
+#define RT_SCHED_COOP_COHERENT 3   /* warp-shared (ray, triangle) pair list tested by all 32 lanes, late re-fill */
+#define RT_SCHED_COOP_INCOHERENT 4 /* same, early re-fill from a pool of prepared rays */
+#define RT_OPT_SCRATCH_ZEROED 1u
+typedef struct rt_trace_opts {
+    float tmax;
+    int32_t schedule;
+    int64_t ray_first;
+    int64_t ray_count;
+    uint32_t flags;
+    int32_t refill_threshold;
+    int32_t tri_threshold;
+    int32_t grid_div;
+    int32_t reserved[4];
+} rt_trace_opts;
 
 const char* rt_last_error(void);
 int rt_abi_version(void);
 /* number of SMs of the current device (0 when there is no device) */
 int rt_device_sm_count(void);
-/* Far end of the ray interval (0, tmax) used by every trace entry point called from this host thread afterwards.
- * Default RT_TMAX_DEFAULT = 1e7, the reference's hard-coded optixTrace tmax (shaders.cu:86). */
-int rt_set_tmax(float tmax);
-float rt_get_tmax(void);
 
 /* ---- BVH build: replaces OptixAccelStructureWrapperCPP::buildAccelStructure
  *      (ray.cpp:27-100) = optixAccelComputeMemoryUsage + optixAccelBuild + optixAccelCompact.
@@ -124,12 +160,14 @@ int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, int64_t n, void* workspace
 /* ---- Trace entry points.  `scratch` = RT_TRACE_SCRATCH_BYTES device bytes private to the call. */
 /* replaces intersectsAny (ray.cpp:161-189; programs shaders.cu:67-89): hit[r] = 1 iff some triangle
  * is hit with 0 < t < 1e7. */
-int rt_trace_any(const void* blob, const rt_ray_desc* rays, uint8_t* hit, void* scratch, void* stream);
+int rt_trace_any(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, uint8_t* hit, void* scratch,
+                 void* stream);
 /* replaces intersectsFirst (ray.cpp:191-219; shaders.cu:93-116): nearest-hit triangle index or -1. */
-int rt_trace_first(const void* blob, const rt_ray_desc* rays, int32_t* tri_idx, void* scratch, void* stream);
+int rt_trace_first(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int32_t* tri_idx, void* scratch,
+                   void* stream);
 /* replaces intersectsClosest (ray.cpp:231-289; shaders.cu:120-172).  Outputs dense in ray order:
  * hit u8, front u8, tri i32 (-1 on miss), loc f32x3 (0 on miss), uv f32x2 = (w0, w1) (0 on miss). */
-int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8_t* hit, uint8_t* front,
+int rt_trace_closest(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, uint8_t* hit, uint8_t* front,
                      int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
 /* Fused ray generation + closest hit: the pinhole rays of the reference's benchmark
  * (gen_rays, test/performance_test.py:10-20: d = normalize(x-(w-1)/2, y-(h-1)/2, -f) @ cam_mat^T, all rays
@@ -140,10 +178,11 @@ typedef struct rt_pinhole {
     float cam_mat[9];   /* row-major 3x3 */
     float origin[3];
 } rt_pinhole;
-int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, uint8_t* hit, uint8_t* front,
-                             int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
+int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, const rt_trace_opts* opts, uint8_t* hit,
+                             uint8_t* front, int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream);
 /* replaces intersectsCount (ray.cpp:291-322; shaders.cu:176-194): exact number of triangles hit. */
-int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream);
+int rt_trace_count(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int32_t* count, void* scratch,
+                   void* stream);
 
 /* ---- Stream compaction: replaces the boolean-mask indexing of ray_optix.py:142-144 / :219-223.
  *      Step 1 scans the hit mask (decoupled look-back), writing one exclusive prefix per
@@ -172,16 +211,18 @@ int rt_compact_scatter_at(const uint8_t* hit, int64_t nray, const void* workspac
  *      reference's count pass + clamp/cumsum (ray.cpp:333-342) + second traversal, in ONE traversal:
  *      step 1 traces once, storing up to max_hits (<= RT_MAX_HITS_LIMIT, reference: 8) hits per ray into
  *      `staging` (nray * max_hits * 16 bytes: tri, x, y, z) and the clamped count per ray, then
- *      scans the counts; step 2 packs them by ray. */
+ *      scans the counts; step 2 packs them by ray.  nray here is the size of the traced WINDOW
+ *      (opts->ray_count): a caller bounds the staging memory by tracing a large batch window by
+ *      window (the Python host does, see ops.intersects_location). */
 int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_bytes, size_t* workspace_bytes);
-int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, int32_t* count_clamped,
-                     void* staging, void* workspace, size_t workspace_bytes, int64_t* total_dev,
-                     void* scratch, void* stream);
+int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int max_hits,
+                     int32_t* count_clamped, void* staging, void* workspace, size_t workspace_bytes,
+                     int64_t* total_dev, void* scratch, void* stream);
 int rt_allhits_scatter(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
                        const void* workspace, float* loc_out, int32_t* ray_idx_out, int32_t* tri_idx_out,
                        void* stream);
 
-/* Sharded variant of rt_allhits_scatter, see rt_compact_scatter_at. */
+/* Sharded / windowed variant of rt_allhits_scatter, see rt_compact_scatter_at. */
 int rt_allhits_scatter_at(int64_t nray, int max_hits, const int32_t* count_clamped, const void* staging,
                           const void* workspace, int64_t ray_base, int ray_idx_bytes, float* loc_out,
                           void* ray_idx_out, int32_t* tri_idx_out, void* stream);
@@ -191,26 +232,38 @@ int rt_allhits_scatter_at(int64_t nray, int max_hits, const int32_t* count_clamp
  *        contain[i] = inside_aabb & odd(+) & odd(-)
  *        broken[i]  = !(odd(+) & odd(-)) & (count(+)==0 | count(-)==0)
  *      flags_dev[0] = any(inside_aabb), flags_dev[1] = any(broken).  `points` describes
- *      the point batch through the origins fields of rt_ray_desc (directions ignored). */
-int rt_contains_parity(const void* blob, const rt_ray_desc* points, const float dir[3],
-                       const float aabb_lo[3], const float aabb_hi[3], uint8_t* contain,
+ *      the point batch through the origins fields of rt_ray_desc (directions ignored).
+ *      `active` (may be NULL) is a per-point mask: only points with active[i] != 0 are traced and
+ *      written, the others keep their contain/broken bytes.  `active` may alias `broken`: the retry of
+ *      ray_optix.py:272-277 (`contains[broken] = contains_points(points[broken], new_dir)`) is then one
+ *      in-place launch with no gather or scatter. */
+int rt_contains_parity(const void* blob, const rt_ray_desc* points, const rt_trace_opts* opts, const float dir[3],
+                       const float aabb_lo[3], const float aabb_hi[3], const uint8_t* active, uint8_t* contain,
                        uint8_t* broken, int32_t* flags_dev, void* scratch, void* stream);
 
 /* ---- Instrumented traversal (same code path, counters compiled in): feeds the
  *      bytes-per-ray figure of the roofline.  mode: 0 closest, 1 any, 2 count.
  *      counters_dev[0] = BVH8 nodes fetched, [1] = triangles fetched, [2] = rays, [3] = hits. */
-int rt_trace_stats(const void* blob, const rt_ray_desc* rays, int mode, uint64_t* counters_dev,
-                   void* scratch, void* stream);
+int rt_trace_stats(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int mode,
+                   uint64_t* counters_dev, void* scratch, void* stream);
 
-/* ---- Host-buffer entry point (end-to-end path): rays and results live in (pinned) HOST memory.
+/* ---- Host-buffer entry points (end-to-end path): rays and results live in (pinned) HOST memory.
  *      Copies ray chunks H2D, traces and copies results D2H on internal streams, overlapping
  *      the three; `dev_work` is caller-provided device memory of rt_host_closest_sizes() bytes.
  *      Synchronous: returns when the results are in the host buffers. */
 int rt_host_closest_sizes(int64_t nray, size_t* dev_work_bytes);
 int rt_host_trace_closest(const void* blob, int64_t nray, const float* h_origins /* [nray,3] or [1,3] */,
                           int origins_broadcast, const float* h_directions /* [nray,3] */,
-                          uint8_t* h_hit, uint8_t* h_front, int32_t* h_tri_idx, float* h_loc, float* h_uv,
-                          void* dev_work, size_t dev_work_bytes);
+                          const rt_trace_opts* opts, uint8_t* h_hit, uint8_t* h_front, int32_t* h_tri_idx,
+                          float* h_loc, float* h_uv, void* dev_work, size_t dev_work_bytes);
+/* Same with stream compaction on the device (intersects_closest(stream_compaction=True), ray_optix.py:139-146):
+ * the dense hit mask h_hit[nray] plus the packed rows of the rays that hit, in ascending ray order:
+ * h_front[h], h_ray_idx[h], h_tri_idx[h], h_loc[h,3], h_uv[h,2]; *n_hit_out = h.  The packed host buffers must
+ * hold nray rows (worst case).  D2H traffic is 1 + 29 * hit_fraction bytes per ray instead of 26. */
+int rt_host_trace_closest_compact(const void* blob, int64_t nray, const float* h_origins, int origins_broadcast,
+                                  const float* h_directions, const rt_trace_opts* opts, uint8_t* h_hit,
+                                  uint8_t* h_front, int32_t* h_ray_idx, int32_t* h_tri_idx, float* h_loc, float* h_uv,
+                                  int64_t* n_hit_out, void* dev_work, size_t dev_work_bytes);
 
 #ifdef __cplusplus
 }

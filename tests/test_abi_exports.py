@@ -38,6 +38,10 @@ def test_struct_layouts_match_the_header():
     from triro.backend import ops
 
     assert C.sizeof(ops.RayDesc) == 8 + 32 + 8 + 32 + 8 + 32          # rt_ray_desc
+    assert C.sizeof(ops.TraceOpts) == 4 + 4 + 8 + 8 + 4 * 4 + 16     # rt_trace_opts
+    assert ops.TraceOpts.ray_first.offset == 8 and ops.TraceOpts.flags.offset == 24
+    o = ops.trace_opts(None, 5, 7)
+    assert (o.tmax, o.ray_first, o.ray_count, o.flags & 1) == (1.0e7, 5, 7, 1) and ops.trace_opts().ray_count == 0     # reference tmax: shaders.cu:86
     hdr = bytes(range(256))
     parsed = ops.parse_header(hdr)
     assert parsed["magic"] == int.from_bytes(hdr[0:4], "little") and parsed["n_tris"] == int.from_bytes(hdr[8:12], "little")
@@ -56,10 +60,10 @@ def test_size_queries_and_argument_validation(lib):
     assert lib.rt_allhits_sizes(1000, 65, C.byref(st), C.byref(w2)) == -1          # RT_MAX_HITS_LIMIT = 64 (reference default 8)
     assert lib.rt_compact_sizes(5000, C.byref(w2)) == 0 and w2.value >= 256 + 2 * 8 * 3
     assert lib.rt_sort_sizes(10_000, C.byref(w2)) == 0 and w2.value >= 10_000 * 12
-    assert lib.rt_abi_version() == 1
-    assert lib.rt_get_tmax() == 1.0e7                                               # reference: shaders.cu:86
-    assert lib.rt_set_tmax(-1.0) == -1 and lib.rt_get_tmax() == 1.0e7
-    assert lib.rt_set_tmax(25.0) == 0 and lib.rt_get_tmax() == 25.0 and lib.rt_set_tmax(1.0e7) == 0
+    assert lib.rt_abi_version() == 2
+    assert not hasattr(lib, "rt_set_tmax"), "tmax is a per-call option (rt_trace_opts), not library state"
+    st_ref = C.c_size_t()
+    assert lib.rt_bvh_refit_sizes(200, C.byref(st_ref)) == 0 and st_ref.value >= (5 * 200 // 8) * 36
 
 
 def test_compute_entry_points_fail_loudly_without_a_device(lib):
@@ -76,8 +80,11 @@ def test_compute_entry_points_fail_loudly_without_a_device(lib):
         rd.shape[i] = s
     buf = (C.c_uint8 * 1024)()
     rd.origins = C.addressof(buf); rd.directions = C.addressof(buf)
-    rc = lib.rt_trace_any(C.addressof(buf), C.byref(rd), C.addressof(buf), C.addressof(buf), None)
+    rc = lib.rt_trace_any(C.addressof(buf), C.byref(rd), None, C.addressof(buf), C.addressof(buf), None)
     assert rc == -2 and b"no CUDA device" in lib.rt_last_error()
+    opts = ops.trace_opts(None, 2, 1)
+    assert lib.rt_trace_any(C.addressof(buf), C.byref(rd), C.byref(opts), C.addressof(buf), C.addressof(buf), None) == -1
+    assert b"ray_first" in lib.rt_last_error()                                  # window outside the 1-ray batch
     rc = lib.rt_bvh_build(C.addressof(buf), 3, C.addressof(buf), 1, None, 0, None, 0, None)
     assert rc == -1                                                            # null blob/workspace
     with pytest.raises((RuntimeError, AssertionError)):

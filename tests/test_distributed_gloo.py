@@ -46,6 +46,19 @@ class OracleBackedLocal:
     def contains_points(self, p, check_direction=None):
         return self._t(self.oi.contains_points(p.numpy(), check_direction))
 
+    def contains_parity(self, points, direction, active=None, out=None):
+        """Stand-in for RayMeshIntersector.contains_parity (the fused kernel): same outputs, masked in-place update."""
+        inside, cp, cm = self.oi.contains_core(points.numpy(), direction)
+        agree = (cp % 2 == 1) & (cm % 2 == 1)
+        contain, broken = self._t(inside & agree), self._t(~agree & ((cp == 0) | (cm == 0)))
+        if active is None:
+            return contain, broken, torch.tensor([int(inside.any()), int(broken.any())], dtype=torch.int32)
+        act = active.clone()
+        flags = torch.tensor([int(inside[act.numpy()].any()), int(broken[act].any())], dtype=torch.int32)
+        out[0][act] = contain[act]
+        out[1][act] = broken[act]
+        return out[0], out[1], flags
+
 
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
@@ -73,6 +86,16 @@ def _worker(rank, world, port, q):
         res["id"] = sh.intersects_id(o, d, return_locations=True, multiple_hits=False)
         pts = (torch.rand((501, 3), generator=torch.Generator().manual_seed(2)) * 2 - 1) * 0.9
         res["contains"] = sh.contains_points(pts, torch.tensor([0.3, 0.5, 0.8]))
+        # default direction on an OPEN mesh (one face removed): some points are 'broken' -> the retry branch; the
+        # decisions are taken over all ranks and the retry direction comes from rank 0, so N ranks == 1 process
+        torch.manual_seed(1234 + rank)           # ranks deliberately disagree about their own RNG
+        open_local = OracleBackedLocal(v, f[1:])
+        sh_open = ShardedRayMeshIntersector(open_local)
+        if rank == 0:
+            torch.manual_seed(77)
+        res["contains_retry"] = sh_open.contains_points(pts * 1.2)
+        # explicit direction with broken points on rank 1's slice only: the reference answers all False everywhere
+        res["contains_quirk"] = sh_open.contains_points(pts * 1.2, torch.tensor([0.3, 0.5, 0.8]))
         part, (lo, hi) = sh.intersects_first(o, d, gather=False)
         assert (lo, hi) == shard_bounds(1001, world, rank) and part.shape == (hi - lo,)
         blob = torch.arange(1000, dtype=torch.uint8) if rank == 0 else None
@@ -109,6 +132,11 @@ def test_two_rank_gather_equals_single_process():
     exp["id"] = (tri, ray, loc)
     pts = (torch.rand((501, 3), generator=torch.Generator().manual_seed(2)) * 2 - 1) * 0.9
     exp["contains"] = (single.contains_points(pts, torch.tensor([0.3, 0.5, 0.8])),)
+    single_open = OracleBackedLocal(v, f[1:])
+    torch.manual_seed(77)
+    exp["contains_retry"] = (single_open.contains_points(pts * 1.2),)
+    assert single_open.oi.contains_core((pts * 1.2).numpy(), single_open.oi.DEFAULT_DIRECTION)[1].size == 501
+    exp["contains_quirk"] = (single_open.contains_points(pts * 1.2, torch.tensor([0.3, 0.5, 0.8])),)
     for k, vals in exp.items():
         assert len(vals) == len(got[k]), k
         for a, b in zip(vals, got[k]):

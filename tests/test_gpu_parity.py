@@ -457,13 +457,17 @@ def test_trace_stats_counts_agree_with_host_simulation(cuda_device):
     v, f = synth.icosphere(4)
     r = make(v, f)
     o, d = synth.readme_rays(200, device=cuda_device)
-    # shared-origin rays take the direct (triangles-in-step) schedule, which visits nodes in exactly
-    # the order of the host simulation; the queued schedule may visit a few more (later tmax shrink)
-    st = hops.trace_stats(r.as_wrapper, o, d, "closest")
+    # the direct (triangles-in-step) schedule visits nodes in exactly the order of the host simulation; the other
+    # schedules test triangles later and may visit a few more nodes (later tmax shrink)
+    old = hops.set_knobs(schedule=hops.SCHED_DIRECT)
+    try:
+        st = hops.trace_stats(r.as_wrapper, o, d, "closest")
+    finally:
+        hops.set_knobs(**old)
     sim = hostsim.trace(r.as_wrapper.blob.cpu().numpy(), "closest", flat(o), flat(d))
     assert st["rays"] == 40_000 and st["nodes"] == sim["stats"]["nodes"] and st["tris"] == sim["stats"]["tris"]
     assert st["hits"] == sim["stats"]["hits"]
-    sq = hops.trace_stats(r.as_wrapper, o.contiguous(), d, "closest")          # per-ray origins -> queued schedule
+    sq = hops.trace_stats(r.as_wrapper, o.contiguous(), d, "closest")          # per-ray origins -> incoherent schedule
     assert sq["rays"] == 40_000 and sq["hits"] == st["hits"] and sq["nodes"] >= st["nodes"]
 
 

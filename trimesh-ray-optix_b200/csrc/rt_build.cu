@@ -74,7 +74,7 @@ struct Workspace {
     uint64_t* keys;
     uint32_t* vals;
     void* sort_ws;
-    uint32_t *left, *right, *first, *last, *parent, *flags, *wide_src;
+    uint32_t *left, *right, *first, *last, *parent, *flags, *wide_src, *wide_parent;
     BBox* box;
     size_t total;
 };
@@ -97,6 +97,7 @@ static Workspace carve_workspace(void* base, int64_t n, uint32_t node_cap) {
     w.last = reinterpret_cast<uint32_t*>(take(ni * 4));
     w.parent = reinterpret_cast<uint32_t*>(take((2 * nn) * 4));
     w.wide_src = reinterpret_cast<uint32_t*>(take((size_t)node_cap * 4));
+    w.wide_parent = reinterpret_cast<uint32_t*>(take((size_t)node_cap * 4));
     w.box = reinterpret_cast<BBox*>(take((2 * nn) * sizeof(BBox)));
     w.total = off;
     return w;
@@ -271,6 +272,21 @@ __global__ void __launch_bounds__(256) k_fill_tris(const float* __restrict__ ver
         fill_tri_record(tris, (uint32_t)i, sorted_prim, verts, nv, faces);
 }
 
+// The (parent << 3 | slot) array of the wide nodes (only rt_bvh_refit reads it) is built in the workspace and placed
+// right behind the nodes actually in use, so that the used prefix of the blob - what travels over NCCL or to disk -
+// is complete: a blob received by broadcast or load can be re-fitted like the original.
+__host__ __device__ inline uint64_t parents_offset_for(uint64_t nodes_offset, uint32_t n_nodes) {
+    return (nodes_offset + (uint64_t)n_nodes * 80u + 255u) / 256u * 256u;
+}
+
+__global__ void __launch_bounds__(256) k_place_parents(uint8_t* blob, const BuildState* st, BlobLayout lay,
+                                                       const uint32_t* __restrict__ wide_parent) {
+    const uint32_t n_nodes = st->node_count < lay.node_cap ? st->node_count : lay.node_cap;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(blob + parents_offset_for(lay.nodes_offset, n_nodes));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += stride) dst[i] = wide_parent[i];
+}
+
 __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n, BlobLayout lay) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     rt_blob_header h;
@@ -283,14 +299,14 @@ __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n,
     h.n_nodes_cap = lay.node_cap;
     h.tris_offset = lay.tris_offset;
     h.nodes_offset = lay.nodes_offset;
-    h.used_bytes = lay.nodes_offset + (uint64_t)h.n_nodes * 80u;
+    h.parents_offset = parents_offset_for(lay.nodes_offset, h.n_nodes);
+    h.used_bytes = (h.parents_offset + (uint64_t)h.n_nodes * 4u + 15u) / 16u * 16u;
     for (int a = 0; a < 3; ++a) {
         h.aabb_lo[a] = n > 0 ? ord2f(st->bounds_lo[a]) : 0.0f;
         h.aabb_hi[a] = n > 0 ? ord2f(st->bounds_hi[a]) : 0.0f;
     }
     h.bad_index_faces = n > 0 ? st->bad_index : 0u;
     h.node_overflow = n > 0 ? (st->node_count > lay.node_cap ? 1u : 0u) : 0u;   // must not happen
-    h.parents_offset = lay.parents_offset;
     *hdr = h;
     if (n == 0) {
         // empty mesh: a root without children, every ray misses
@@ -298,7 +314,7 @@ __global__ void k_finalize(rt_blob_header* hdr, const BuildState* st, int64_t n,
         memset(&nd, 0, sizeof(nd));
         nd.ex = nd.ey = nd.ez = 1;   // imask = trimask = 0: no slot is ever reported
         *reinterpret_cast<Node8*>(reinterpret_cast<uint8_t*>(hdr) + lay.nodes_offset) = nd;
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(hdr) + lay.parents_offset) = 0xffffffffu;
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(hdr) + h.parents_offset) = 0xffffffffu;
     }
 }
 
@@ -371,7 +387,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting();
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
-        o.parent = reinterpret_cast<uint32_t*>(blob8 + lay.parents_offset);
+        o.parent = w.wide_parent;
         o.node_count = &w.state->node_count; o.tri_count = &w.state->tri_count; o.node_cap = lay.node_cap;
         int per_sm = 0;
         RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse, 128, 0));
@@ -383,6 +399,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         void* args[] = {&t, &o, (void*)&vertices, (void*)&n_verts, (void*)&faces, &stp};
         RT_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(cgrid), dim3(128), args, 0, stream));
         k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.vals, blob8 + lay.tris_offset);
+        k_place_parents<<<grid_for(lay.node_cap, 256, dev.sm_count, 4), 256, 0, stream>>>(blob8, w.state, lay, w.wide_parent);
     }
     k_finalize<<<1, 32, 0, stream>>>(hdr, w.state, n, lay);
     RT_CUDA_TRY(cudaGetLastError());
@@ -447,7 +464,8 @@ __global__ void __launch_bounds__(128) k_refit_nodes(rt_blob_header* hdr, BBox* 
 
 extern "C" int rt_bvh_refit_sizes(int64_t n_faces, size_t* workspace_bytes) {
     RT_REQUIRE(n_faces >= 0 && n_faces <= (int64_t)1 << 30 && workspace_bytes, RT_ERR_INVALID, "rt_bvh_refit_sizes: bad arguments");
-    *workspace_bytes = carve_refit(nullptr, blob_layout(n_faces).node_cap).total;
+    // bound for any leaf size the blob may have been built with (the node count itself is only known on the device)
+    *workspace_bytes = carve_refit(nullptr, wide_node_cap(n_faces, 1)).total;
     return RT_OK;
 }
 
@@ -458,21 +476,23 @@ extern "C" int rt_bvh_refit(const float* vertices, int64_t n_verts, const int32_
     RT_REQUIRE(blob && workspace, RT_ERR_INVALID, "rt_bvh_refit: null blob/workspace");
     RT_REQUIRE(((uintptr_t)blob & 255) == 0 && ((uintptr_t)workspace & 255) == 0, RT_ERR_INVALID,
                "rt_bvh_refit: blob and workspace must be 256-byte aligned");
-    const BlobLayout lay = blob_layout(n_faces);
-    RT_REQUIRE(blob_bytes >= lay.total_bytes, RT_ERR_SIZE,
-               "rt_bvh_refit: blob %zu < %zu (refit needs the complete blob of rt_bvh_build, not its used prefix)", blob_bytes,
-               lay.total_bytes);
-    RefitWorkspace w = carve_refit(workspace, lay.node_cap);
+    // The kernels take every offset and count from the blob's own header (so a blob that arrived by NCCL broadcast or
+    // from disk - just its used prefix - re-fits like the original, whatever leaf size it was built with); the host
+    // can only bound the sizes: header + triangle records + one node + its parent word.
+    const uint32_t node_cap = wide_node_cap(n_faces, 1);
+    RT_REQUIRE(blob_bytes >= RT_BLOB_HEADER_BYTES + (size_t)n_faces * 48u + 84u, RT_ERR_SIZE,
+               "rt_bvh_refit: blob of %zu bytes cannot hold %lld triangles", blob_bytes, (long long)n_faces);
+    RefitWorkspace w = carve_refit(workspace, node_cap);
     RT_REQUIRE(workspace_bytes >= w.total, RT_ERR_SIZE, "rt_bvh_refit: workspace %zu < %zu", workspace_bytes, w.total);
     if (n_faces == 0) return RT_OK;
     RT_REQUIRE(vertices && faces && n_verts > 0, RT_ERR_INVALID, "rt_bvh_refit: null vertices/faces");
     DeviceInfo dev;
     RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "rt_bvh_refit: no CUDA device");
     uint8_t* blob8 = reinterpret_cast<uint8_t*>(blob);
-    RT_CUDA_TRY(cudaMemsetAsync(w.counters, 0, align_up_sz((size_t)lay.node_cap * 4u, 256), stream));
+    RT_CUDA_TRY(cudaMemsetAsync(w.counters, 0, align_up_sz((size_t)node_cap * 4u, 256), stream));
     k_refit_tris<<<grid_for(n_faces, 256, dev.sm_count, 8), 256, 0, stream>>>(vertices, n_verts, faces, n_faces,
-                                                                              blob8 + lay.tris_offset);
-    k_refit_nodes<<<grid_for(lay.node_cap, 128, dev.sm_count, 8), 128, 0, stream>>>(reinterpret_cast<rt_blob_header*>(blob8),
+                                                                              blob8 + RT_BLOB_HEADER_BYTES);
+    k_refit_nodes<<<grid_for(node_cap, 128, dev.sm_count, 8), 128, 0, stream>>>(reinterpret_cast<rt_blob_header*>(blob8),
                                                                                     w.node_box, w.counters);
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;

@@ -247,13 +247,10 @@ inline cudaError_t sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, void* w
     if (hist_blocks < 1) hist_blocks = 1;
     k_histogram<<<hist_blocks, 256, 0, stream>>>(keys, n, w.hist);
     k_scan_hist<<<kPasses, kRadix, 0, stream>>>(w.hist);
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(PassSmem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // opt-in to > 48 KB of dynamic shared memory: a per-device (per-context) attribute, so it is set on every call
+    // (cheap) rather than once per process - a second GPU in the same process needs it too
+    e = cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
     uint64_t* kin = keys; uint32_t* vin = vals;
     uint64_t* kout = w.keys_alt; uint32_t* vout = w.vals_alt;
     for (int p = 0; p < kPasses; ++p) {

@@ -25,6 +25,8 @@ constexpr int kTraceThreads = 128;
 struct TraceParams {
     const uint8_t* blob;
     rt_ray_desc rays;
+    int64_t ray_first;           // window [ray_first, ray_first + nray) of the descriptor's index space; outputs are
+    int64_t nray;                // indexed by (ray - ray_first)
     int o_mode, d_mode;          // kGeneral / kPacked (offset 3*r) / kConstant (offset 0) / kGeneral32
     int refill_threshold, tri_threshold;
     float tmax;
@@ -42,6 +44,7 @@ struct TraceParams {
     uint4* staging;
     // contains
     float dir[3], aabb_lo[3], aabb_hi[3];
+    const uint8_t* active;       // optional per-point mask (may alias `broken`)
     uint8_t* contain;
     uint8_t* broken;
     int32_t* flags;
@@ -58,6 +61,11 @@ struct LocalStack {
     __device__ __forceinline__ void push(int sp, uint32_t x, uint32_t y) { e[sp] = make_uint2(x, y); }
     __device__ __forceinline__ void pop(int sp, uint32_t& x, uint32_t& y) { const uint2 v = e[sp]; x = v.x; y = v.y; }
 };
+
+// Every launch leaves its scratch zeroed: the last CTA to finish resets the ray counter and the CTA count, so the
+// next call on the same stream can skip its memset (RT_OPT_SCRATCH_ZEROED) and a launch is a single kernel.
+struct TraceParams;
+__device__ __forceinline__ void release_scratch(const TraceParams& p);
 
 enum FetchMode { kGeneral = 0, kPacked = 1, kConstant = 2, kGeneral32 = 3, kPinhole = 4 };
 
@@ -81,8 +89,9 @@ __device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int6
 // of contains_points, or a pinhole camera ray generated in registers (reference gen_rays,
 // test/performance_test.py:10-20: d = normalize(x - (w-1)/2, y - (h-1)/2, -f) @ cam_mat^T).
 template <int MODE>
-__device__ __forceinline__ void load_ray(const TraceParams& p, int64_t r, float& ox, float& oy, float& oz, float& dx,
+__device__ __forceinline__ void load_ray(const TraceParams& p, int64_t r_local, float& ox, float& oy, float& oz, float& dx,
                                          float& dy, float& dz) {
+    const int64_t r = r_local + p.ray_first;     // index in the descriptor's space (rt_trace_opts::ray_first)
     if (p.o_mode == kPinhole) {
         const long long y = r / p.cam_w, x = r - y * p.cam_w;
         const float px = (float)x - p.cam_half_w, py = (float)y - p.cam_half_h, pz = -p.cam_f;
@@ -153,6 +162,9 @@ constexpr int kRefillThresholdDirect = 8;
 constexpr int kQueueCap = 32;
 constexpr int kQueueHigh = kQueueCap - kNodeMaxTris;   // 8: above this a lane may not take a node step
 constexpr int kTriThreshold = 8;
+// warp-cooperative schedules (rt_trace_coop.cuh): pairs listed before the warp tests them
+constexpr int kPairThresholdCoherent = 16;
+constexpr int kPairThresholdIncoherent = 32;
 constexpr int kPoolWords = 13;   // prepared ray: o, S, o permuted, 1/d, packed (kzf | octinv << 8)
 
 struct LaneQueue {
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
     const uint8_t* nodes = p.blob + hdr->nodes_offset;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t nray = p.rays.nray;
+    const int64_t nray = p.nray;
     LocalStack stack;
     LaneQueue queue;
     queue.q = s_queue;
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                         phase = 0;
                         nodes_done = false;
                         active = true;
+                        if constexpr (MODE == kContains) { if (p.active && !p.active[r]) active = false; }   // masked-out point
                     }
                     __syncwarp();
                     pool_head += take; pool_count -= take;
@@ -399,11 +412,15 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
                             phase = 0;
                             nodes_done = false;
                             active = true;
+                            if constexpr (MODE == kContains) { if (p.active && !p.active[r]) active = false; }
                         }
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (!__any_sync(0xffffffffu, active)) {
+                if (exhausted && pool_count == 0) break;
+                continue;      // every lane drew a masked-out point (contains with `active`): draw again
+            }
         }
 
         if constexpr (!QUEUED) {
@@ -447,7 +464,24 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(co
             atomicAdd(&p.counters[3], st_hits);
         }
     }
+    release_scratch(p);
 }
+
+__device__ __forceinline__ void release_scratch(const TraceParams& p) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* done = reinterpret_cast<unsigned int*>(p.ray_counter + 1);
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+            atomicExch(p.ray_counter, 0ull);
+            atomicExch(done, 0u);
+        }
+    }
+}
+
+}  // namespace rt
+#include "rt_trace_coop.cuh"
+namespace rt {
 
 static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t nray);
 static bool is_packed(const int64_t shape[4], const int64_t stride[4]) {
@@ -469,14 +503,6 @@ static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t n
     return nray < ((int64_t)1 << 31) ? kGeneral32 : kGeneral;
 }
 
-static thread_local float g_tmax = RT_TMAX_DEFAULT;
-
-static int env_int(const char* name, int fallback, int lo, int hi) {
-    const char* e = getenv(name);
-    int v = e ? atoi(e) : fallback;
-    return v < lo ? lo : (v > hi ? hi : v);
-}
-
 static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
     RT_REQUIRE(rays != nullptr, RT_ERR_INVALID, "%s: null ray descriptor", fn);
     RT_REQUIRE(rays->nray >= 0, RT_ERR_INVALID, "%s: negative ray count", fn);
@@ -493,9 +519,28 @@ static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
     return RT_OK;
 }
 
+// resident CTAs per SM of every kernel variant, per device (filled on first use; benign race: same value)
+constexpr int kMaxDevices = 64;
+static int g_per_sm[kMaxDevices][4][2][8];
+
 template <int MODE, bool STATS>
-static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray_desc* rays, void* scratch,
-                  cudaStream_t stream) {
+static int occupancy(int sched, int* per_sm) {
+    switch (sched) {
+        case RT_SCHED_DIRECT: return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace<MODE, STATS, false>, kTraceThreads, 0);
+        case RT_SCHED_QUEUED: return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace<MODE, STATS, true>, kTraceThreads, 0);
+        default:
+            if constexpr (MODE != kAllHits) {
+                if (sched == RT_SCHED_COOP_COHERENT)
+                    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, false>, kTraceThreads, 0);
+                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, true>, kTraceThreads, 0);
+            }
+            return (int)cudaErrorInvalidValue;
+    }
+}
+
+template <int MODE, bool STATS>
+static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts,
+                  void* scratch, cudaStream_t stream) {
     RT_REQUIRE(blob != nullptr && ((uintptr_t)blob & 15) == 0, RT_ERR_INVALID, "%s: blob null or not 16-byte aligned", fn);
     RT_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 7) == 0, RT_ERR_INVALID, "%s: scratch null or misaligned", fn);
     const bool pinhole = p.o_mode == kPinhole;     // preset by rt_trace_closest_pinhole: rays are generated, not fetched
@@ -503,42 +548,65 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
         const int rc = check_rays(fn, rays, MODE != kContains);
         if (rc != RT_OK) return rc;
     }
-    if (rays->nray == 0) return RT_OK;
+    static const rt_trace_opts kDefaults = {};
+    const rt_trace_opts& o = opts ? *opts : kDefaults;
+    RT_REQUIRE(o.ray_first >= 0 && o.ray_first <= rays->nray, RT_ERR_INVALID, "%s: ray_first %lld outside [0, %lld]", fn,
+               (long long)o.ray_first, (long long)rays->nray);
+    const int64_t count = o.ray_count <= 0 ? rays->nray - o.ray_first : o.ray_count;     // 0 (zero-initialised opts) = all
+    RT_REQUIRE(count <= rays->nray - o.ray_first, RT_ERR_INVALID, "%s: ray window [%lld, +%lld) exceeds the batch of %lld", fn,
+               (long long)o.ray_first, (long long)count, (long long)rays->nray);
+    if (count == 0) return RT_OK;
     DeviceInfo dev;
     RT_REQUIRE(device_info(&dev) == RT_OK && dev.sm_count > 0, RT_ERR_CUDA, "%s: no CUDA device", fn);
     p.blob = reinterpret_cast<const uint8_t*>(blob);
     p.rays = *rays;
+    p.ray_first = o.ray_first;
+    p.nray = count;
     if (!pinhole) {
         p.o_mode = fetch_mode(rays->shape, rays->o_stride, rays->nray);
         p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
     }
-    p.tmax = g_tmax;
+    p.tmax = o.tmax > 0.0f ? o.tmax : RT_TMAX_DEFAULT;     // NaN and <= 0 select the reference's 1e7
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
-    RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
-    // Scheduling heuristic: rays that share one origin (a stride-0 broadcast, i.e. camera / primary
-    // rays, reference README.md:38 and test/performance_test.py:36-41) are coherent and mostly
-    // short: test triangles inside the node step and re-fill lanes late.  Anything else is treated
-    // as incoherent: postponed triangle tests, early re-fill.  TRIRO_TRI_MODE=0/1 overrides.
-    const int queued_default = (MODE != kContains && (p.o_mode == kConstant || pinhole)) ? 0 : 1;
-    const bool queued = env_int("TRIRO_TRI_MODE", queued_default, 0, 1) != 0;
-    p.refill_threshold = env_int("TRIRO_REFILL_THRESHOLD", queued ? kRefillThresholdQueued : kRefillThresholdDirect, 1, 32);
-    p.tri_threshold = env_int("TRIRO_TRI_THRESHOLD", kTriThreshold, 1, 32);
-    static thread_local int per_sm_cache[2][2][8] = {{{0}}};
-    int& per_sm = per_sm_cache[queued ? 1 : 0][STATS ? 1 : 0][MODE];
+    if (!(o.flags & RT_OPT_SCRATCH_ZEROED)) RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
+    // Scheduling: rays that share one origin (a stride-0 broadcast, i.e. camera / primary rays, reference
+    // README.md:38 and test/performance_test.py:36-41) are coherent and mostly short: lanes re-fill late.
+    // Anything else is treated as incoherent: rays prepared 32 at a time into a pool, early re-fill.  Both use
+    // the warp-cooperative triangle tests of rt_trace_coop.cuh; all-hits keeps the per-lane queues.
+    const bool coherent = MODE != kContains && (p.o_mode == kConstant || pinhole);
+    int sched = o.schedule;
+    RT_REQUIRE(sched >= RT_SCHED_AUTO && sched <= RT_SCHED_COOP_INCOHERENT, RT_ERR_INVALID, "%s: unknown schedule %d", fn, sched);
+    if (sched == RT_SCHED_AUTO) sched = coherent ? RT_SCHED_COOP_COHERENT : RT_SCHED_COOP_INCOHERENT;
+    if (MODE == kAllHits && sched >= RT_SCHED_COOP_COHERENT) sched = sched == RT_SCHED_COOP_COHERENT ? RT_SCHED_DIRECT : RT_SCHED_QUEUED;
+    const bool early = sched == RT_SCHED_QUEUED || sched == RT_SCHED_COOP_INCOHERENT;
+    const bool coop = sched >= RT_SCHED_COOP_COHERENT;
+    auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    p.refill_threshold = o.refill_threshold > 0 ? clampi(o.refill_threshold, 1, 32)
+                                                : (early ? kRefillThresholdQueued : kRefillThresholdDirect);
+    p.tri_threshold = o.tri_threshold > 0 ? clampi(o.tri_threshold, 1, coop ? kPairCap - 32 : 32)
+                                          : (coop ? (early ? kPairThresholdIncoherent : kPairThresholdCoherent) : kTriThreshold);
+    RT_REQUIRE(dev.device >= 0 && dev.device < kMaxDevices, RT_ERR_CUDA, "%s: device index %d not supported", fn, dev.device);
+    int& per_sm = g_per_sm[dev.device][sched - 1][STATS ? 1 : 0][MODE];
     if (per_sm == 0) {
-        if (queued)
-            RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS, true>, kTraceThreads, 0));
-        else
-            RT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, STATS, false>, kTraceThreads, 0));
-        RT_REQUIRE(per_sm > 0, RT_ERR_CUDA, "%s: kernel does not fit an SM", fn);
+        int v = 0;
+        const int oc = occupancy<MODE, STATS>(sched, &v);
+        RT_REQUIRE(oc == (int)cudaSuccess && v > 0, RT_ERR_CUDA, "%s: kernel does not fit an SM", fn);
+        per_sm = v;
     }
     int64_t grid = (int64_t)dev.sm_count * per_sm;
-    const int64_t rays_per_cta = (int64_t)kTraceThreads * env_int("TRIRO_GRID_DIV", 1, 1, 64);
-    const int64_t need = (rays->nray + rays_per_cta - 1) / rays_per_cta;
+    const int64_t rays_per_cta = (int64_t)kTraceThreads * clampi(o.grid_div > 0 ? o.grid_div : 1, 1, 64);
+    const int64_t need = (count + rays_per_cta - 1) / rays_per_cta;
     if (grid > need) grid = need;
-    if (queued) k_trace<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
-    else k_trace<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+    switch (sched) {
+        case RT_SCHED_DIRECT: k_trace<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p); break;
+        case RT_SCHED_QUEUED: k_trace<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p); break;
+        default:
+            if constexpr (MODE != kAllHits) {
+                if (sched == RT_SCHED_COOP_COHERENT) k_trace_coop<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+                else k_trace_coop<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            }
+    }
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }
@@ -547,38 +615,34 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
 
 using namespace rt;
 
-extern "C" int rt_set_tmax(float tmax) {
-    RT_REQUIRE(tmax > 0.0f, RT_ERR_INVALID, "rt_set_tmax: tmax must be positive (got %g)", (double)tmax);
-    g_tmax = tmax;
-    return RT_OK;
-}
-extern "C" float rt_get_tmax(void) { return g_tmax; }
-
-extern "C" int rt_trace_any(const void* blob, const rt_ray_desc* rays, uint8_t* hit, void* scratch, void* stream) {
+extern "C" int rt_trace_any(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, uint8_t* hit, void* scratch,
+                            void* stream) {
     RT_REQUIRE(hit || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_any: null output");
     TraceParams p = {};
     p.hit = hit;
-    return launch<kAny, false>("rt_trace_any", p, blob, rays, scratch, (cudaStream_t)stream);
+    return launch<kAny, false>("rt_trace_any", p, blob, rays, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_trace_first(const void* blob, const rt_ray_desc* rays, int32_t* tri_idx, void* scratch, void* stream) {
+extern "C" int rt_trace_first(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int32_t* tri_idx,
+                              void* scratch, void* stream) {
     RT_REQUIRE(tri_idx || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_first: null output");
     TraceParams p = {};
     p.tri = tri_idx;
-    return launch<kFirst, false>("rt_trace_first", p, blob, rays, scratch, (cudaStream_t)stream);
+    return launch<kFirst, false>("rt_trace_first", p, blob, rays, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_trace_closest(const void* blob, const rt_ray_desc* rays, uint8_t* hit, uint8_t* front,
-                                int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream) {
+extern "C" int rt_trace_closest(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, uint8_t* hit,
+                                uint8_t* front, int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream) {
     RT_REQUIRE((hit && front && tri_idx && loc && uv) || (rays && rays->nray == 0), RT_ERR_INVALID,
                "rt_trace_closest: null output");
     TraceParams p = {};
     p.hit = hit; p.front = front; p.tri = tri_idx; p.loc = loc; p.uv = uv;
-    return launch<kClosest, false>("rt_trace_closest", p, blob, rays, scratch, (cudaStream_t)stream);
+    return launch<kClosest, false>("rt_trace_closest", p, blob, rays, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, uint8_t* hit, uint8_t* front,
-                                        int32_t* tri_idx, float* loc, float* uv, void* scratch, void* stream) {
+extern "C" int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam, const rt_trace_opts* opts, uint8_t* hit,
+                                        uint8_t* front, int32_t* tri_idx, float* loc, float* uv, void* scratch,
+                                        void* stream) {
     RT_REQUIRE(cam != nullptr && cam->width > 0 && cam->height > 0 && cam->focal > 0.0f, RT_ERR_INVALID,
                "rt_trace_closest_pinhole: bad camera");
     RT_REQUIRE(hit && front && tri_idx && loc && uv, RT_ERR_INVALID, "rt_trace_closest_pinhole: null output");
@@ -592,39 +656,40 @@ extern "C" int rt_trace_closest_pinhole(const void* blob, const rt_pinhole* cam,
     rt_ray_desc rd = {};
     rd.nray = cam->width * cam->height;
     rd.shape[0] = 1; rd.shape[1] = cam->height; rd.shape[2] = cam->width; rd.shape[3] = 3;
-    return launch<kClosest, false>("rt_trace_closest_pinhole", p, blob, &rd, scratch, (cudaStream_t)stream);
+    return launch<kClosest, false>("rt_trace_closest_pinhole", p, blob, &rd, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_trace_count(const void* blob, const rt_ray_desc* rays, int32_t* count, void* scratch, void* stream) {
+extern "C" int rt_trace_count(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int32_t* count,
+                              void* scratch, void* stream) {
     RT_REQUIRE(count || (rays && rays->nray == 0), RT_ERR_INVALID, "rt_trace_count: null output");
     TraceParams p = {};
     p.count = count;
-    return launch<kCount, false>("rt_trace_count", p, blob, rays, scratch, (cudaStream_t)stream);
+    return launch<kCount, false>("rt_trace_count", p, blob, rays, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_contains_parity(const void* blob, const rt_ray_desc* points, const float dir[3],
-                                  const float aabb_lo[3], const float aabb_hi[3], uint8_t* contain, uint8_t* broken,
-                                  int32_t* flags_dev, void* scratch, void* stream) {
+extern "C" int rt_contains_parity(const void* blob, const rt_ray_desc* points, const rt_trace_opts* opts, const float dir[3],
+                                  const float aabb_lo[3], const float aabb_hi[3], const uint8_t* active, uint8_t* contain,
+                                  uint8_t* broken, int32_t* flags_dev, void* scratch, void* stream) {
     RT_REQUIRE(dir && aabb_lo && aabb_hi && flags_dev, RT_ERR_INVALID, "rt_contains_parity: null argument");
     RT_REQUIRE((contain && broken) || (points && points->nray == 0), RT_ERR_INVALID,
                "rt_contains_parity: null output");
     TraceParams p = {};
     for (int a = 0; a < 3; ++a) { p.dir[a] = dir[a]; p.aabb_lo[a] = aabb_lo[a]; p.aabb_hi[a] = aabb_hi[a]; }
-    p.contain = contain; p.broken = broken; p.flags = flags_dev;
+    p.active = active; p.contain = contain; p.broken = broken; p.flags = flags_dev;
     RT_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
-    return launch<kContains, false>("rt_contains_parity", p, blob, points, scratch, (cudaStream_t)stream);
+    return launch<kContains, false>("rt_contains_parity", p, blob, points, opts, scratch, (cudaStream_t)stream);
 }
 
-extern "C" int rt_trace_stats(const void* blob, const rt_ray_desc* rays, int mode, uint64_t* counters_dev,
-                              void* scratch, void* stream) {
+extern "C" int rt_trace_stats(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int mode,
+                              uint64_t* counters_dev, void* scratch, void* stream) {
     RT_REQUIRE(counters_dev != nullptr, RT_ERR_INVALID, "rt_trace_stats: null counters");
     RT_CUDA_TRY(cudaMemsetAsync(counters_dev, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
     TraceParams p = {};
     p.counters = reinterpret_cast<unsigned long long*>(counters_dev);
     switch (mode) {
-        case 0: return launch<kClosest, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
-        case 1: return launch<kAny, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
-        case 2: return launch<kCount, true>("rt_trace_stats", p, blob, rays, scratch, (cudaStream_t)stream);
+        case 0: return launch<kClosest, true>("rt_trace_stats", p, blob, rays, opts, scratch, (cudaStream_t)stream);
+        case 1: return launch<kAny, true>("rt_trace_stats", p, blob, rays, opts, scratch, (cudaStream_t)stream);
+        case 2: return launch<kCount, true>("rt_trace_stats", p, blob, rays, opts, scratch, (cudaStream_t)stream);
         default: return set_error(RT_ERR_INVALID, "rt_trace_stats: mode must be 0 (closest), 1 (any) or 2 (count)");
     }
 }
@@ -644,16 +709,16 @@ extern "C" int rt_allhits_sizes(int64_t nray, int max_hits, size_t* staging_byte
     return RT_OK;
 }
 
-extern "C" int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, int max_hits, int32_t* count_clamped,
-                                void* staging, void* workspace, size_t workspace_bytes, int64_t* total_dev,
-                                void* scratch, void* stream) {
+extern "C" int rt_allhits_trace(const void* blob, const rt_ray_desc* rays, const rt_trace_opts* opts, int max_hits,
+                                int32_t* count_clamped, void* staging, void* workspace, size_t workspace_bytes,
+                                int64_t* total_dev, void* scratch, void* stream) {
     RT_REQUIRE(max_hits >= 1 && max_hits <= RT_MAX_HITS_LIMIT, RT_ERR_INVALID, "rt_allhits_trace: max_hits out of range");
     RT_REQUIRE(total_dev != nullptr, RT_ERR_INVALID, "rt_allhits_trace: null total");
     RT_REQUIRE((count_clamped && staging && workspace) || (rays && rays->nray == 0), RT_ERR_INVALID,
                "rt_allhits_trace: null buffer");
     TraceParams p = {};
     p.count = count_clamped; p.max_hits = max_hits; p.staging = reinterpret_cast<uint4*>(staging);
-    const int rc = launch<kAllHits, false>("rt_allhits_trace", p, blob, rays, scratch, (cudaStream_t)stream);
+    const int rc = launch<kAllHits, false>("rt_allhits_trace", p, blob, rays, opts, scratch, (cudaStream_t)stream);
     if (rc != RT_OK) return rc;
-    return scan_counts_i32(count_clamped, rays->nray, workspace, workspace_bytes, total_dev, (cudaStream_t)stream);
+    return scan_counts_i32(count_clamped, p.nray, workspace, workspace_bytes, total_dev, (cudaStream_t)stream);
 }

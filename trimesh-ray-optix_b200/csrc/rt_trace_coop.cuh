@@ -1,0 +1,340 @@
+// rt_trace_coop.cuh — traversal kernel with WARP-COOPERATIVE triangle tests (included by rt_trace.cu).
+//
+// Same role as k_trace (rt_trace.cu): replaces optixTrace + the closest/first/any/count programs of the
+// reference (triro/backend/shaders.cu:67-194) and the two count launches of contains_points
+// (triro/ray/ray_optix.py:254-260).  What differs from k_trace is WHO tests a triangle:
+//
+//   * every lane still owns one ray and walks the BVH8 one wide node per step, but a hit leaf slot is
+//     not tested by the lane that found it.  The lane appends (lane, triangle record) pairs to a list
+//     shared by the warp; when the list is long enough (or lanes wait to retire) ALL 32 lanes test
+//     pairs, whichever ray they belong to.  The part of the ray the triangle test needs (shear S,
+//     permuted origin, kz) lives in shared memory, column = lane, so any lane can read any ray
+//     without bank conflicts;
+//   * results merge through shared memory: closest hit is a 64-bit atomicMin on
+//     (float bits of t << 32 | primitive index) — t > 0, so the bit pattern orders like the value and
+//     equal t resolves to the smaller primitive index, exactly the rule of ClosestVisitor — count is a
+//     32-bit atomicAdd, any-hit a flag;
+//   * the lane whose pair wins computes location / uv / front right there, at the width of the pair
+//     batch, and parks them in shared memory; retiring a ray is then a plain copy (k_trace re-fetches
+//     and re-tests the winning triangle with the few lanes that retire together).
+//
+// ncu of k_trace on config 2 (profiles/r1_ncu_regions_config2_v4.txt): the in-step triangle test was
+// 27.8 % of all warp instructions at 8.17 of 32 active lanes.  Results are bit-identical to k_trace
+// (tests/test_gpu_parity.py::test_all_schedules_give_identical_results).
+#pragma once
+
+namespace rt {
+
+constexpr int kPairCap = 128;          // pairs a warp can hold; a node step of 32 lanes appends 32 per round
+constexpr int kRayWords = 7;           // resident part of a ray in shared memory: S(3), permuted origin(3), kzf
+
+// POOL = incoherent batches: rays are prepared 32 at a time into a shared-memory pool and lanes re-fill early;
+// otherwise lanes re-fill late and set their ray up in place (coherent batches).
+template <int MODE, bool STATS, bool POOL>
+__global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_coop(const __grid_constant__ TraceParams p) {
+    static_assert(MODE != kAllHits, "all-hits keeps the per-lane schedule (deterministic record order)");
+    constexpr bool kKey = MODE == kClosest || MODE == kFirst;
+    __shared__ float s_ray[kRayWords][kTraceThreads];
+    __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim
+    __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
+    __shared__ float s_attr[MODE == kClosest ? 6 : 1][kTraceThreads];    // loc(3), uv(2), front
+    __shared__ uint32_t s_pair[kTraceThreads / 32][kPairCap];
+    __shared__ uint8_t s_plane[kTraceThreads / 32][kPairCap];
+    __shared__ float s_pool[POOL ? kPoolWords : 1][kTraceThreads];
+    init_mask_luts();
+    const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
+    const uint8_t* tris = p.blob + hdr->tris_offset;
+    const uint8_t* nodes = p.blob + hdr->nodes_offset;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col0 = (int)(threadIdx.x & ~31u), mycol = (int)threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t nray = p.nray;
+    const unsigned long long key_init = (unsigned long long)__float_as_uint(p.tmax) << 32;
+    LocalStack stack;
+    unsigned long long st_nodes = 0, st_tris = 0, st_rays = 0, st_hits = 0;
+    bool any_inside = false, any_broken = false;
+
+    Trav tv;
+    Ray ray;                          // only o, 1/d, octinv, magic stay live across iterations
+    float tmax = p.tmax;
+    int64_t r = -1;
+    bool active = false, exhausted = false, nodes_done = true;
+    int phase = 0;
+    uint32_t count_plus = 0;
+    int n_pend = 0;                   // pairs in the warp's list (warp-uniform)
+    int my_pend = 0;                  // of which belong to this lane's ray
+    int pool_head = 0, pool_count = 0;
+    int64_t pool_base = 0;
+    uint32_t ty = 0u, tx = 0u, tmask = 0u;      // triangles of this lane's last node step not yet listed
+    trav_init(tv);
+
+    // ---- test every listed pair with the whole warp
+    auto flush = [&]() {
+        __syncwarp();
+        for (int base = 0; base < n_pend; base += 32) {
+            const int i = base + lane;
+            bool won = false;
+            unsigned long long key = 0;
+            int col = 0;
+            TriHit h;
+            Ray t;
+            float v0x = 0, v0y = 0, v0z = 0, v1x = 0, v1y = 0, v1z = 0, v2x = 0, v2y = 0, v2z = 0;
+            if (i < n_pend) {
+                const uint32_t slot = s_pair[warp][i];
+                col = col0 + (int)s_plane[warp][i];
+                t.Sx = s_ray[0][col]; t.Sy = s_ray[1][col]; t.Sz = s_ray[2][col];
+                t.okx = s_ray[3][col]; t.oky = s_ray[4][col]; t.okz = s_ray[5][col];
+                t.kzf = __float_as_int(s_ray[6][col]);
+                const uint8_t* tp = tris + (size_t)slot * 48u;
+                const U4 a = ldg128(tp), b = ldg128(tp + 16), c = ldg128(tp + 32);
+                v0x = as_float(a.x); v0y = as_float(a.y); v0z = as_float(a.z);
+                v1x = as_float(b.x); v1y = as_float(b.y); v1z = as_float(b.z);
+                v2x = as_float(c.x); v2y = as_float(c.y); v2z = as_float(c.z);
+                if (STATS) ++st_tris;
+                if (tri_test(t, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h) && h.t > 0.0f) {
+                    if constexpr (kKey) {
+                        key = ((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned long long)(uint32_t)a.w;
+                        if (key < s_best[col]) { atomicMin(&s_best[col], key); won = true; }
+                    } else if constexpr (MODE == kAny) {
+                        if (h.t < p.tmax) s_cnt[col] = 1u;
+                    } else {
+                        if (h.t < p.tmax) atomicAdd(&s_cnt[col], 1u);
+                    }
+                }
+            }
+            if constexpr (MODE == kClosest) {
+                __syncwarp();
+                if (won && s_best[col] == key) {     // this pair is the ray's nearest so far: its lane computes the attributes
+                    const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+                    s_attr[0][col] = at.lx; s_attr[1][col] = at.ly; s_attr[2][col] = at.lz;
+                    s_attr[3][col] = at.uv0; s_attr[4][col] = at.uv1;
+                    s_attr[5][col] = tri_front(t, h) ? 1.0f : 0.0f;
+                }
+            }
+        }
+        __syncwarp();
+        n_pend = 0; my_pend = 0;
+        if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[mycol] >> 32));
+        if constexpr (MODE == kAny) { if (active && s_cnt[mycol]) { nodes_done = true; ty = 0u; } }   // early exit
+    };
+
+    // ---- start ray r on this lane from a prepared set-up
+    auto start_ray = [&](const Ray& t) {
+        s_ray[0][mycol] = t.Sx; s_ray[1][mycol] = t.Sy; s_ray[2][mycol] = t.Sz;
+        s_ray[3][mycol] = t.okx; s_ray[4][mycol] = t.oky; s_ray[5][mycol] = t.okz;
+        s_ray[6][mycol] = __int_as_float(t.kzf);
+        if constexpr (kKey) s_best[mycol] = key_init; else s_cnt[mycol] = 0u;
+        tmax = p.tmax;
+        trav_init(tv);
+        nodes_done = false;
+        active = true;
+    };
+
+    for (;;) {
+        // ---- 1. flush policy (the ONE place pairs are tested), retirement, re-fill
+        const unsigned done_mask = __ballot_sync(0xffffffffu, !active || nodes_done);
+        const int busy = 32 - __popc(done_mask);
+        const bool want_refill = done_mask != 0u && busy < ((exhausted && pool_count == 0) ? 1 : p.refill_threshold);
+        const unsigned unlisted = __ballot_sync(0xffffffffu, ty != 0u);
+        if (n_pend > 0 && (n_pend >= p.tri_threshold || (unlisted != 0u && n_pend + 32 > kPairCap) ||
+                           (want_refill && __any_sync(0xffffffffu, active && nodes_done && my_pend > 0))))
+            flush();
+        if (want_refill) {
+            if (active && nodes_done && my_pend == 0 && ty == 0u) {
+                if constexpr (MODE == kClosest || MODE == kFirst) {
+                    const unsigned long long best = s_best[mycol];
+                    const bool hit = best != key_init;
+                    if (STATS) { ++st_rays; st_hits += hit; }
+                    if (MODE == kFirst) {
+                        if (p.tri) p.tri[r] = hit ? (int32_t)(uint32_t)best : -1;
+                    } else if (p.hit) {
+                        // miss: reference miss program shaders.cu:128-135
+                        p.hit[r] = hit ? 1 : 0;
+                        p.front[r] = hit ? (s_attr[5][mycol] != 0.0f ? 1 : 0) : 0;
+                        p.tri[r] = hit ? (int32_t)(uint32_t)best : -1;
+                        p.loc[3 * r] = hit ? s_attr[0][mycol] : 0.f; p.loc[3 * r + 1] = hit ? s_attr[1][mycol] : 0.f;
+                        p.loc[3 * r + 2] = hit ? s_attr[2][mycol] : 0.f;
+                        p.uv[2 * r] = hit ? s_attr[3][mycol] : 0.f; p.uv[2 * r + 1] = hit ? s_attr[4][mycol] : 0.f;
+                    }
+                    active = false;
+                } else if constexpr (MODE == kAny) {
+                    const bool found = s_cnt[mycol] != 0u;
+                    if (STATS) { ++st_rays; st_hits += found; }
+                    if (p.hit) p.hit[r] = found ? 1 : 0;
+                    active = false;
+                } else if constexpr (MODE == kCount) {
+                    const uint32_t c = s_cnt[mycol];
+                    if (STATS) { ++st_rays; st_hits += c > 0u; }
+                    if (p.count) p.count[r] = (int32_t)c;
+                    active = false;
+                } else if constexpr (MODE == kContains) {
+                    // reference: ray_optix.py:238-267 — count along +dir, then along -dir
+                    const uint32_t c = s_cnt[mycol];
+                    if (phase == 0) {
+                        count_plus = c;
+                        Ray t;
+                        ray_setup(t, ray.ox, ray.oy, ray.oz, -p.dir[0], -p.dir[1], -p.dir[2]);
+                        ray.idx = t.idx; ray.idy = t.idy; ray.idz = t.idz; ray.octinv = t.octinv;
+                        start_ray(t);
+                        phase = 1;
+                    } else {
+                        const bool inside = ray.ox > p.aabb_lo[0] && ray.oy > p.aabb_lo[1] && ray.oz > p.aabb_lo[2] &&
+                                            ray.ox < p.aabb_hi[0] && ray.oy < p.aabb_hi[1] && ray.oz < p.aabb_hi[2];
+                        const bool agree = (count_plus & 1u) && (c & 1u);
+                        const bool brk = !agree && (count_plus == 0u || c == 0u);
+                        p.contain[r] = (inside && agree) ? 1 : 0;
+                        p.broken[r] = brk ? 1 : 0;
+                        any_inside |= inside;
+                        any_broken |= brk;
+                        active = false;
+                    }
+                }
+            }
+            if constexpr (POOL) {
+                for (;;) {
+                    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+                    if (idle == 0u) break;
+                    if (pool_count == 0) {
+                        if (exhausted) break;
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(p.ray_counter, 32ull);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        int64_t n = nray - (int64_t)base;
+                        if (n <= 32) exhausted = true;
+                        if (n <= 0) break;
+                        if (n > 32) n = 32;
+                        if (lane < n) {
+                            float ox, oy, oz, dx, dy, dz;
+                            load_ray<MODE>(p, (int64_t)base + lane, ox, oy, oz, dx, dy, dz);
+                            Ray t;
+                            ray_setup(t, ox, oy, oz, dx, dy, dz);
+                            int skip = 0;
+                            if constexpr (MODE == kContains) { if (p.active && !p.active[(int64_t)base + lane]) skip = 1; }
+                            const int col = col0 + lane;
+                            s_pool[0][col] = t.ox; s_pool[1][col] = t.oy; s_pool[2][col] = t.oz;
+                            s_pool[3][col] = t.Sx; s_pool[4][col] = t.Sy; s_pool[5][col] = t.Sz;
+                            s_pool[6][col] = t.okx; s_pool[7][col] = t.oky; s_pool[8][col] = t.okz;
+                            s_pool[9][col] = t.idx; s_pool[10][col] = t.idy; s_pool[11][col] = t.idz;
+                            s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8) | (skip << 16));
+                        }
+                        __syncwarp();
+                        pool_base = (int64_t)base; pool_head = 0; pool_count = (int)n;
+                    }
+                    const int n_idle = __popc(idle);
+                    const int take = n_idle < pool_count ? n_idle : pool_count;
+                    const int my = __popc(idle & lt_mask);
+                    if (!active && my < take) {
+                        const int col = col0 + pool_head + my;
+                        const int packed = __float_as_int(s_pool[12][col]);
+                        if (!(packed >> 16)) {
+                            r = pool_base + pool_head + my;
+                            Ray t;
+                            ray.ox = s_pool[0][col]; ray.oy = s_pool[1][col]; ray.oz = s_pool[2][col];
+                            t.Sx = s_pool[3][col]; t.Sy = s_pool[4][col]; t.Sz = s_pool[5][col];
+                            t.okx = s_pool[6][col]; t.oky = s_pool[7][col]; t.okz = s_pool[8][col];
+                            ray.idx = s_pool[9][col]; ray.idy = s_pool[10][col]; ray.idz = s_pool[11][col];
+                            t.kzf = packed & 0xff; ray.octinv = ((uint32_t)packed >> 8) & 0xffu;
+                            ray.magic = p.byte_magic;
+                            phase = 0;
+                            start_ray(t);
+                        }
+                    }
+                    __syncwarp();
+                    pool_head += take; pool_count -= take;
+                }
+            } else {
+                const unsigned idle = __ballot_sync(0xffffffffu, !active);
+                if (idle != 0u && !exhausted) {
+                    const int n_idle = __popc(idle);
+                    const int leader = __ffs((int)idle) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(p.ray_counter, (unsigned long long)n_idle);
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if ((int64_t)base + n_idle >= nray) exhausted = true;
+                    if (!active) {
+                        r = (int64_t)base + __popc(idle & lt_mask);
+                        bool take = r < nray;
+                        if constexpr (MODE == kContains) { if (take && p.active && !p.active[r]) take = false; }
+                        if (take) {
+                            float ox, oy, oz, dx, dy, dz;
+                            load_ray<MODE>(p, r, ox, oy, oz, dx, dy, dz);
+                            Ray t;
+                            ray_setup(t, ox, oy, oz, dx, dy, dz);
+                            ray.ox = t.ox; ray.oy = t.oy; ray.oz = t.oz;
+                            ray.idx = t.idx; ray.idy = t.idy; ray.idz = t.idz; ray.octinv = t.octinv;
+                            ray.magic = p.byte_magic;
+                            phase = 0;
+                            start_ray(t);
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (exhausted && pool_count == 0) break;
+                continue;      // every lane drew a masked-out point: draw again
+            }
+        }
+
+        // ---- 2. node phase: one wide node per lane; hit leaf slots yield a 24-bit triangle mask
+        if (active && !nodes_done && ty == 0u) {
+            if (tv.gy & 0xff000000u) {
+                const uint32_t hits = tv.gy;
+                const int bit = 31 - clz32(hits);
+                tv.gy &= ~(1u << bit);
+                if (tv.gy & 0xff000000u) { stack.push(tv.sp, tv.gx, tv.gy); ++tv.sp; }
+                const uint32_t slot = (uint32_t)(bit - 24) ^ ray.octinv;
+                const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot));
+                const uint8_t* np = nodes + (size_t)(tv.gx + rel) * 80u;
+                const U4 n0 = ldg128(np), n1 = ldg128(np + 16), n2 = ldg128(np + 32), n3 = ldg128(np + 48),
+                         n4 = ldg128(np + 64);
+                if (STATS) ++st_nodes;
+                const uint32_t hm = node_test(ray, n0, n1, n2, n3, n4, 0.0f, tmax);
+                tv.gx = n1.x;
+                tv.gy = (hm & 0xff000000u) | (n0.w >> 24);
+                ty = hm & 0x00ffffffu; tx = n1.y; tmask = n1.z;
+            }
+            if (!(tv.gy & 0xff000000u)) {
+                if (tv.sp == 0) nodes_done = true;
+                else { --tv.sp; stack.pop(tv.sp, tv.gx, tv.gy); }
+            }
+        }
+
+        // ---- 3. append (lane, triangle) pairs to the warp's list, one per lane and round; what does not fit
+        //         stays in ty and is listed after the next flush (such a lane takes no node step meanwhile)
+        unsigned has = __ballot_sync(0xffffffffu, ty != 0u);
+        while (has != 0u && n_pend + 32 <= kPairCap) {
+            if (ty != 0u) {
+                const int b = ffs32(ty) - 1;
+                ty &= ty - 1u;
+                const int pos = n_pend + __popc(has & lt_mask);
+                s_pair[warp][pos] = tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b));
+                s_plane[warp][pos] = (uint8_t)lane;
+                ++my_pend;
+            }
+            n_pend += __popc(has);
+            has = __ballot_sync(0xffffffffu, ty != 0u);
+        }
+    }
+    if (MODE == kContains) {
+        if (__any_sync(0xffffffffu, any_inside) && lane == 0) atomicOr(&p.flags[0], 1);
+        if (__any_sync(0xffffffffu, any_broken) && lane == 0) atomicOr(&p.flags[1], 1);
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_nodes += __shfl_xor_sync(0xffffffffu, st_nodes, o);
+            st_tris += __shfl_xor_sync(0xffffffffu, st_tris, o);
+            st_rays += __shfl_xor_sync(0xffffffffu, st_rays, o);
+            st_hits += __shfl_xor_sync(0xffffffffu, st_hits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&p.counters[0], st_nodes);
+            atomicAdd(&p.counters[1], st_tris);
+            atomicAdd(&p.counters[2], st_rays);
+            atomicAdd(&p.counters[3], st_hits);
+        }
+    }
+    release_scratch(p);
+}
+
+}  // namespace rt

@@ -14,7 +14,6 @@ from __future__ import annotations
 import ctypes as C
 import os
 import struct
-import threading
 from typing import Tuple
 
 import torch
@@ -28,6 +27,8 @@ BLOB_HEADER_BYTES = 256
 BLOB_MAGIC = 0x38485642
 MAX_DEPTH = 60               # rt_core.cuh kMaxDepth
 HOST_CHUNK = 1 << 20
+ABI_VERSION = 2
+ALLHITS_STAGING_BYTES = 1 << 30   # all-hits staging per launch window (nray_window * max_hits * 16 B)
 
 _lib = None
 
@@ -45,6 +46,18 @@ class RayDesc(C.Structure):
     ]
 
 
+class TraceOpts(C.Structure):
+    """rt_trace_opts — per-call options of every trace entry point (include/raymesh_b200.h)."""
+
+    _fields_ = [("tmax", C.c_float), ("schedule", C.c_int32), ("ray_first", C.c_int64), ("ray_count", C.c_int64),
+                ("flags", C.c_uint32), ("refill_threshold", C.c_int32), ("tri_threshold", C.c_int32),
+                ("grid_div", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+SCHED_AUTO, SCHED_DIRECT, SCHED_QUEUED, SCHED_COOP_COHERENT, SCHED_COOP_INCOHERENT = 0, 1, 2, 3, 4
+OPT_SCRATCH_ZEROED = 1
+
+
 class Pinhole(C.Structure):
     """rt_pinhole — camera of the fused ray-generation entry point."""
 
@@ -56,36 +69,36 @@ def _declare(lib):
     vp, i64, sz, ci = C.c_void_p, C.c_int64, C.c_size_t, C.c_int
     psz = C.POINTER(C.c_size_t)
     prd = C.POINTER(RayDesc)
+    pto = C.POINTER(TraceOpts)
+    pf = C.POINTER(C.c_float)
     sig = {
         "rt_last_error": (C.c_char_p, []),
         "rt_abi_version": (ci, []),
         "rt_device_sm_count": (ci, []),
-        "rt_set_tmax": (ci, [C.c_float]),
-        "rt_get_tmax": (C.c_float, []),
         "rt_bvh_sizes": (ci, [i64, i64, psz, psz]),
         "rt_bvh_build": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
         "rt_bvh_refit_sizes": (ci, [i64, psz]),
         "rt_bvh_refit": (ci, [vp, i64, vp, i64, vp, sz, vp, sz, vp]),
         "rt_sort_sizes": (ci, [i64, psz]),
         "rt_sort_pairs_u64": (ci, [vp, vp, i64, vp, sz, vp]),
-        "rt_trace_any": (ci, [vp, prd, vp, vp, vp]),
-        "rt_trace_first": (ci, [vp, prd, vp, vp, vp]),
-        "rt_trace_closest": (ci, [vp, prd, vp, vp, vp, vp, vp, vp, vp]),
-        "rt_trace_count": (ci, [vp, prd, vp, vp, vp]),
-        "rt_trace_closest_pinhole": (ci, [vp, C.POINTER(Pinhole), vp, vp, vp, vp, vp, vp, vp]),
+        "rt_trace_any": (ci, [vp, prd, pto, vp, vp, vp]),
+        "rt_trace_first": (ci, [vp, prd, pto, vp, vp, vp]),
+        "rt_trace_closest": (ci, [vp, prd, pto, vp, vp, vp, vp, vp, vp, vp]),
+        "rt_trace_count": (ci, [vp, prd, pto, vp, vp, vp]),
+        "rt_trace_closest_pinhole": (ci, [vp, C.POINTER(Pinhole), pto, vp, vp, vp, vp, vp, vp, vp]),
         "rt_compact_sizes": (ci, [i64, psz]),
         "rt_compact_scan": (ci, [vp, i64, vp, sz, vp, vp]),
         "rt_compact_scatter": (ci, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rt_allhits_sizes": (ci, [i64, ci, psz, psz]),
-        "rt_allhits_trace": (ci, [vp, prd, ci, vp, vp, vp, sz, vp, vp, vp]),
+        "rt_allhits_trace": (ci, [vp, prd, pto, ci, vp, vp, vp, sz, vp, vp, vp]),
         "rt_allhits_scatter": (ci, [i64, ci, vp, vp, vp, vp, vp, vp, vp]),
         "rt_allhits_scatter_at": (ci, [i64, ci, vp, vp, vp, i64, ci, vp, vp, vp, vp]),
         "rt_compact_scatter_at": (ci, [vp, i64, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, vp]),
-        "rt_contains_parity": (ci, [vp, prd, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
-                                    vp, vp, vp]),
-        "rt_trace_stats": (ci, [vp, prd, ci, vp, vp, vp]),
+        "rt_contains_parity": (ci, [vp, prd, pto, pf, pf, pf, vp, vp, vp, vp, vp, vp]),
+        "rt_trace_stats": (ci, [vp, prd, pto, ci, vp, vp, vp]),
         "rt_host_closest_sizes": (ci, [i64, psz]),
-        "rt_host_trace_closest": (ci, [vp, i64, vp, ci, vp, vp, vp, vp, vp, vp, vp, sz]),
+        "rt_host_trace_closest": (ci, [vp, i64, vp, ci, vp, pto, vp, vp, vp, vp, vp, vp, sz]),
+        "rt_host_trace_closest_compact": (ci, [vp, i64, vp, ci, vp, pto, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64), vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly
@@ -109,8 +122,8 @@ def get_module():
             "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
     lib = C.CDLL(path)
     EXPORTS = _declare(lib)
-    if lib.rt_abi_version() != 1:
-        raise RuntimeError(f"{path}: ABI version {lib.rt_abi_version()} != 1")
+    if lib.rt_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {lib.rt_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return _lib
 
@@ -148,24 +161,62 @@ def _check(rc: int, what: str):
 
 TMAX_DEFAULT = 1.0e7        # reference: tmax of every optixTrace, shaders.cu:86
 MAX_HITS_LIMIT = 64
-_tls = threading.local()
 
 
-def _apply_tmax(accel) -> None:
-    """The C ABI keeps the far end of the ray interval per host thread (rt_set_tmax); push the accel's value when it
-    differs from what this thread set last.  Default 1e7 = the reference's hard-coded value."""
-    t = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT))
-    if getattr(_tls, "tmax", TMAX_DEFAULT) != t:
-        _check(get_module().rt_set_tmax(t), "rt_set_tmax")
-        _tls.tmax = t
+def _env_int(name: str) -> int:
+    try:
+        return int(os.environ.get(name, "0"))
+    except ValueError:
+        return 0
+
+
+# Scheduling knobs for experiments (tools/), read ONCE at import; 0 = the library's defaults.  The C library itself
+# reads no environment variable on the trace path: everything a launch depends on is in rt_trace_opts.
+_KNOBS = dict(schedule=_env_int("TRIRO_SCHED"), refill_threshold=_env_int("TRIRO_REFILL_THRESHOLD"),
+              tri_threshold=_env_int("TRIRO_TRI_THRESHOLD"), grid_div=_env_int("TRIRO_GRID_DIV"))
+
+
+def set_knobs(**kw) -> dict:
+    """Override the experiment knobs (schedule, refill_threshold, tri_threshold, grid_div) for later calls of this
+    process; returns the previous values.  Every schedule gives bit-identical results."""
+    old = dict(_KNOBS)
+    for k, v in kw.items():
+        if k not in _KNOBS:
+            raise KeyError(k)
+        _KNOBS[k] = int(v)
+    return old
+
+
+def trace_opts(accel=None, ray_first: int = 0, ray_count: int = -1, scratch_zeroed: bool = True) -> TraceOpts:
+    """rt_trace_opts of one call: the accel's tmax (default 1e7 = the reference's hard-coded value), the ray window,
+    and the experiment knobs."""
+    o = TraceOpts()
+    o.tmax = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
+    o.schedule = _KNOBS["schedule"]
+    o.ray_first, o.ray_count = int(ray_first), max(int(ray_count), 0)     # 0 = up to the end of the batch
+    o.flags = OPT_SCRATCH_ZEROED if scratch_zeroed else 0
+    o.refill_threshold, o.tri_threshold, o.grid_div = _KNOBS["refill_threshold"], _KNOBS["tri_threshold"], _KNOBS["grid_div"]
+    return o
 
 
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_scratch_cache: dict = {}
+
+
 def _scratch(device) -> torch.Tensor:
-    return torch.empty(TRACE_SCRATCH_BYTES, dtype=torch.uint8, device=device)
+    """RT_TRACE_SCRATCH_BYTES of zeroed device memory private to (device, current stream).  Every launch leaves its
+    scratch zeroed again (the last CTA resets it), so with RT_OPT_SCRATCH_ZEROED a trace call is exactly one kernel
+    launch; launches that share a scratch are ordered by their stream."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
+    t = _scratch_cache.get(key)
+    if t is None:
+        t = torch.zeros(TRACE_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
+        _scratch_cache[key] = t
+    return t
 
 
 def _ptr(t: torch.Tensor | None):
@@ -236,6 +287,8 @@ class AccelStructure:
         lib = get_module()
         if not (vertices.is_cuda and faces.is_cuda):
             raise ValueError("vertices and faces must reside in cuda device.")
+        if vertices.device != faces.device:
+            raise ValueError("vertices and faces must be on the same device")
         if vertices.dtype != torch.float32 or faces.dtype != torch.int32:
             raise ValueError("vertices must be float32 and faces int32")
         if vertices.dim() != 2 or vertices.shape[1] != 3 or faces.dim() != 2 or faces.shape[1] != 3:
@@ -265,22 +318,22 @@ class AccelStructure:
             raise RuntimeError("rt_bvh_build produced an invalid blob header")
         if hdr["bad_index_faces"]:
             raise ValueError(f"{hdr['bad_index_faces']} faces reference vertices outside [0, {nv})")
-        if hdr["node_overflow"]:
-            raise RuntimeError("BVH node pool overflow (internal error)")
-        if hdr["depth"] > MAX_DEPTH:
-            raise RuntimeError(f"BVH depth {hdr['depth']} exceeds the traversal stack ({MAX_DEPTH}); mesh too degenerate")
+        validate_header(hdr, blob.numel())
         self.blob = blob
         self.header = hdr
         return self
 
     def refit(self, vertices: torch.Tensor, faces: torch.Tensor):
         """Same topology, new vertex positions: rewrite the triangle records and re-fit all node
-        boxes bottom-up in place (rt_bvh_refit) — no sort, no hierarchy emission."""
+        boxes bottom-up in place (rt_bvh_refit) — no sort, no hierarchy emission.  Works on any valid blob
+        (built here, received by broadcast, loaded from disk): the used prefix carries the parent links."""
         lib = get_module()
         if self.blob is None:
             raise RuntimeError("acceleration structure has not been built")
         if vertices.dtype != torch.float32 or faces.dtype != torch.int32 or not (vertices.is_cuda and faces.is_cuda):
             raise ValueError("vertices must be float32 and faces int32 CUDA tensors")
+        if vertices.device != self.blob.device or faces.device != self.blob.device:
+            raise ValueError(f"refit: vertices / faces must be on the blob's device {self.blob.device}")
         if faces.shape[0] != self.header["n_tris"]:
             raise ValueError(f"refit needs the same topology: {faces.shape[0]} faces, BVH was built for {self.header['n_tris']}")
         vertices = vertices.contiguous()
@@ -296,26 +349,33 @@ class AccelStructure:
         return self
 
     def save(self, path: str):
-        """Serialise the used prefix of the blob (header + triangles + nodes)."""
-        torch.save({"format": "triro_b200_bvh8", "abi_version": 1, "blob": self.used().cpu()}, path)
+        """Serialise the used prefix of the blob (header + triangles + nodes + parent links)."""
+        torch.save({"format": "triro_b200_bvh8", "abi_version": ABI_VERSION, "blob": self.used().cpu()}, path)
 
     def load(self, path: str, device="cuda"):
         d = torch.load(path, map_location="cpu")
-        if d.get("format") != "triro_b200_bvh8" or d.get("abi_version") != 1:
+        if d.get("format") != "triro_b200_bvh8" or d.get("abi_version") != ABI_VERSION:
             raise ValueError(f"{path} is not a BVH blob of this ABI version")
         return self.adopt(d["blob"].to(device))
 
     def adopt(self, blob: torch.Tensor):
-        """Attach to a blob received from elsewhere (NCCL broadcast, torch.load)."""
+        """Attach to a blob received from elsewhere (NCCL broadcast, torch.load).  The header is validated against
+        the tensor exactly like a freshly built one: a truncated, foreign or corrupt blob is refused here instead of
+        overrunning the traversal stack or reading out of bounds in a kernel."""
+        if blob.dtype != torch.uint8 or blob.dim() != 1 or blob.numel() < BLOB_HEADER_BYTES or not blob.is_contiguous():
+            raise ValueError("a BVH blob is a contiguous 1-D uint8 tensor of at least 256 bytes")
+        if blob.is_cuda and blob.data_ptr() % 256 != 0:
+            raise ValueError("a BVH blob must be 256-byte aligned")
         hdr = parse_header(blob[:BLOB_HEADER_BYTES].cpu().numpy().tobytes())
-        if hdr["magic"] != BLOB_MAGIC or hdr["abi_version"] != 1:
+        if hdr["magic"] != BLOB_MAGIC or hdr["abi_version"] != ABI_VERSION:
             raise ValueError("not a BVH blob of this ABI version")
+        validate_header(hdr, blob.numel())
         self.blob = blob
         self.header = hdr
         return self
 
     def used(self) -> torch.Tensor:
-        """Prefix of the blob that must travel (header + triangles + nodes in use)."""
+        """Prefix of the blob that must travel (header + triangles + nodes in use + their parent links)."""
         return self.blob[: self.header["used_bytes"]]
 
     def free(self):
@@ -334,10 +394,27 @@ def parse_header(raw: bytes) -> dict:
                 bad_index_faces=bad, node_overflow=overflow, parents_offset=parents_off)
 
 
-def _blob_of(accel) -> torch.Tensor:
+def validate_header(hdr: dict, blob_bytes: int) -> None:
+    """What the build path guarantees, checked for every blob before a kernel may walk it."""
+    if hdr["node_overflow"]:
+        raise RuntimeError("BVH node pool overflow (internal error)")
+    if hdr["depth"] > MAX_DEPTH:
+        raise RuntimeError(f"BVH depth {hdr['depth']} exceeds the traversal stack ({MAX_DEPTH}); mesh too degenerate")
+    nt, nn = hdr["n_tris"], hdr["n_nodes"]
+    ok = (nn >= 1 and hdr["tris_offset"] == BLOB_HEADER_BYTES and hdr["tris_offset"] % 16 == 0
+          and hdr["nodes_offset"] % 16 == 0 and hdr["nodes_offset"] >= hdr["tris_offset"] + 48 * nt
+          and hdr["parents_offset"] % 4 == 0 and hdr["parents_offset"] >= hdr["nodes_offset"] + 80 * nn
+          and hdr["used_bytes"] >= hdr["parents_offset"] + 4 * nn and hdr["used_bytes"] <= blob_bytes)
+    if not ok:
+        raise ValueError(f"inconsistent BVH blob header for a tensor of {blob_bytes} bytes (truncated or corrupt blob)")
+
+
+def _blob_of(accel, device=None) -> torch.Tensor:
     inner = getattr(accel, "_inner", accel)
     if inner.blob is None:
         raise RuntimeError("acceleration structure has not been built")
+    if device is not None and inner.blob.device != device:
+        raise ValueError(f"the acceleration structure lives on {inner.blob.device} but the rays are on {device}")
     return inner.blob
 
 
@@ -345,38 +422,38 @@ def _blob_of(accel) -> torch.Tensor:
 def intersects_any(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     """Bool[*b]: does each ray hit anything with 0 < t < 1e7 (reference ops.py:84-101)."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
         out = torch.empty(batch, dtype=torch.bool, device=dev)
-        _check(get_module().rt_trace_any(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
-               "rt_trace_any")
+        _check(get_module().rt_trace_any(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
+                                         _ptr(_scratch(dev)), _stream(dev)), "rt_trace_any")
     return out
 
 
 def intersects_first(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     """Int32[*b]: index of the nearest hit triangle or -1 (reference ops.py:104-119)."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
         out = torch.empty(batch, dtype=torch.int32, device=dev)
-        _check(get_module().rt_trace_first(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
-               "rt_trace_first")
+        _check(get_module().rt_trace_first(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
+                                           _ptr(_scratch(dev)), _stream(dev)), "rt_trace_first")
     return out
 
 
-def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tensor):
+def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, ray_first: int = 0, ray_count: int = -1):
     """(hit Bool[*b], front Bool[*b], tri Int32[*b], loc Float32[*b,3], uv Float32[*b,2])
-    (reference ops.py:122-149, ray.cpp:231-289)."""
+    (reference ops.py:122-149, ray.cpp:231-289).  With a ray window [ray_first, ray_first + ray_count) of the
+    flattened batch only those rays are traced and the outputs are 1-D over the window."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
+    if ray_first != 0 or ray_count >= 0:
+        batch = (_window(rd.nray, ray_first, ray_count),)
     dev = origins.device
     with torch.cuda.device(dev):
         hit = torch.empty(batch, dtype=torch.bool, device=dev)
@@ -384,26 +461,37 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
         tri = torch.empty(batch, dtype=torch.int32, device=dev)
         loc = torch.empty((*batch, 3), dtype=torch.float32, device=dev)
         uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
-        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc),
-                                             _ptr(uv), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest")
+        if hit.numel() == 0:
+            return hit, front, tri, loc, uv
+        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure, ray_first, ray_count)),
+                                             _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc), _ptr(uv), _ptr(_scratch(dev)),
+                                             _stream(dev)), "rt_trace_closest")
     return hit, front, tri, loc, uv
 
 
+def _window(nray: int, ray_first: int, ray_count: int) -> int:
+    if ray_first < 0 or ray_first > nray or (ray_count >= 0 and ray_first + ray_count > nray):
+        raise ValueError(f"ray window [{ray_first}, +{ray_count}) outside the batch of {nray} rays")
+    return nray - ray_first if ray_count < 0 else ray_count
+
+
 def intersects_closest_into(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, hit_ptr: int, front_ptr: int,
-                            tri_ptr: int, loc_ptr: int, uv_ptr: int) -> None:
+                            tri_ptr: int, loc_ptr: int, uv_ptr: int, ray_first: int = 0, ray_count: int = -1) -> None:
     """rt_trace_closest with caller-provided RAW output addresses (u8 hit, u8 front, i32 tri, f32 loc[3], f32 uv[2]
     per ray, dense).  The addresses may be peer-GPU memory mapped into this process (NVLink P2P / symmetric
     memory): the kernel then stores its results straight into another rank's tensors - the fused trace + gather
     of triro.distributed.  Asynchronous on the current stream."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
+    if _window(rd.nray, ray_first, ray_count) == 0:
+        return
     with torch.cuda.device(dev):
-        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), C.c_void_p(hit_ptr), C.c_void_p(front_ptr),
-                                             C.c_void_p(tri_ptr), C.c_void_p(loc_ptr), C.c_void_p(uv_ptr),
-                                             _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest")
+        _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure, ray_first, ray_count)),
+                                             C.c_void_p(hit_ptr), C.c_void_p(front_ptr), C.c_void_p(tri_ptr),
+                                             C.c_void_p(loc_ptr), C.c_void_p(uv_ptr), _ptr(_scratch(dev)), _stream(dev)),
+               "rt_trace_closest")
 
 
 def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int, height: int, focal: float):
@@ -411,7 +499,6 @@ def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int,
     test/performance_test.py:10-20) generated inside the kernel: no ray tensors are built or read.
     Returns (hit[h,w], front[h,w], tri[h,w], loc[h,w,3], uv[h,w,2])."""
     blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
     dev = blob.device
     cam = Pinhole()
     cam.width, cam.height, cam.focal = int(width), int(height), float(focal)
@@ -430,8 +517,9 @@ def intersects_closest_pinhole(accel_structure, cam_mat, cam_origin, width: int,
         tri = torch.empty(batch, dtype=torch.int32, device=dev)
         loc = torch.empty((*batch, 3), dtype=torch.float32, device=dev)
         uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
-        _check(get_module().rt_trace_closest_pinhole(_ptr(blob), C.byref(cam), _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc),
-                                                     _ptr(uv), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_closest_pinhole")
+        _check(get_module().rt_trace_closest_pinhole(_ptr(blob), C.byref(cam), C.byref(trace_opts(accel_structure)), _ptr(hit),
+                                                     _ptr(front), _ptr(tri), _ptr(loc), _ptr(uv), _ptr(_scratch(dev)),
+                                                     _stream(dev)), "rt_trace_closest_pinhole")
     return hit, front, tri, loc, uv
 
 
@@ -487,15 +575,22 @@ def compact_scatter_at(hit, ws, front, tri, loc, uv, ray_base: int, ray_idx_byte
                                                   C.c_void_p(uv_ptr), _stream(dev)), "rt_compact_scatter_at")
 
 
-def allhits_trace(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = 8):
-    """First half of intersects_location: one traversal + scan -> (state for allhits_scatter_at, number of hits)."""
+def allhits_window_rays(max_hits: int, budget_bytes: int | None = None) -> int:
+    """Rays per all-hits launch so that the staging buffer (rays * max_hits * 16 B) stays within `budget_bytes`."""
+    budget = ALLHITS_STAGING_BYTES if budget_bytes is None else int(budget_bytes)
+    return max(1024, budget // (16 * max_hits))
+
+
+def allhits_trace(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = 8, ray_first: int = 0,
+                  ray_count: int = -1):
+    """First half of intersects_location for one ray window: one traversal + scan -> (state for allhits_scatter_at,
+    number of hits)."""
     tensor_input_check(origins, dirs)
     lib = get_module()
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
-    n = rd.nray
+    n = _window(rd.nray, ray_first, ray_count)
     with torch.cuda.device(dev):
         st_b, ws_b = C.c_size_t(), C.c_size_t()
         _check(lib.rt_allhits_sizes(n, max_hits, C.byref(st_b), C.byref(ws_b)), "rt_allhits_sizes")
@@ -503,8 +598,11 @@ def allhits_trace(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, ma
         ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
         counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         total = torch.zeros(1, dtype=torch.int64, device=dev)
-        _check(lib.rt_allhits_trace(_ptr(blob), C.byref(rd), max_hits, _ptr(counts), _ptr(staging), _ptr(ws), ws.numel(),
-                                    _ptr(total), _ptr(_scratch(dev)), _stream(dev)), "rt_allhits_trace")
+        if n == 0:
+            return (0, max_hits, counts, staging, ws), 0
+        _check(lib.rt_allhits_trace(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure, ray_first, n)), max_hits,
+                                    _ptr(counts), _ptr(staging), _ptr(ws), ws.numel(), _ptr(total), _ptr(_scratch(dev)),
+                                    _stream(dev)), "rt_allhits_trace")
         return (n, max_hits, counts, staging, ws), int(total.item())
 
 
@@ -520,78 +618,97 @@ def allhits_scatter_at(state, ray_base: int, ray_idx_bytes: int, loc_ptr: int, r
 def intersects_count(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     """Int32[*b]: number of triangles hit with 0 < t < 1e7 (reference ops.py:152-168)."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
         out = torch.empty(batch, dtype=torch.int32, device=dev)
-        _check(get_module().rt_trace_count(_ptr(blob), C.byref(rd), _ptr(out), _ptr(_scratch(dev)), _stream(dev)),
-               "rt_trace_count")
+        _check(get_module().rt_trace_count(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
+                                           _ptr(_scratch(dev)), _stream(dev)), "rt_trace_count")
     return out
 
 
-def intersects_location(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = MAX_ANYHIT_SIZE):
+def intersects_location(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, max_hits: int = MAX_ANYHIT_SIZE,
+                        ray_idx_base: int = 0, ray_idx_dtype=torch.int32, staging_bytes: int | None = None,
+                        ray_first: int = 0, ray_count: int = -1):
     """(loc Float32[h,3], ray_idx Int32[h], tri_idx Int32[h]): up to 8 hits per ray, grouped by
     ray in ascending ray order (reference ops.py:171-192, ray.cpp:324-378) — one traversal
-    instead of the reference's two."""
+    instead of the reference's two.
+
+    The reference sizes its output from a count pass; here hits are staged at max_hits * 16 B per ray during the
+    single traversal, so a large batch is traced window by window (rt_trace_opts.ray_first / ray_count: no copy of
+    the rays, any strides) with at most ALLHITS_STAGING_BYTES of staging alive; the windows' packed results are
+    concatenated, which preserves the ray order.  Ray indices are `ray_idx_base` + the index in the flattened batch;
+    `ray_first` / `ray_count` restrict the call to a slice of the batch (sharded callers)."""
     tensor_input_check(origins, dirs)
-    lib = get_module()
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
-    n = rd.nray
+    n = _window(rd.nray, ray_first, ray_count)
+    rb = 8 if ray_idx_dtype == torch.int64 else 4
+    per = allhits_window_rays(max_hits, staging_bytes)
+    parts = []
     with torch.cuda.device(dev):
-        st_b, ws_b = C.c_size_t(), C.c_size_t()
-        _check(lib.rt_allhits_sizes(n, max_hits, C.byref(st_b), C.byref(ws_b)), "rt_allhits_sizes")
-        staging = torch.empty(max(st_b.value, 16), dtype=torch.uint8, device=dev)
-        ws = torch.empty(max(ws_b.value, 256), dtype=torch.uint8, device=dev)
-        counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        total = torch.empty(1, dtype=torch.int64, device=dev)
-        _check(lib.rt_allhits_trace(_ptr(blob), C.byref(rd), max_hits, _ptr(counts), _ptr(staging), _ptr(ws), ws.numel(),
-                                    _ptr(total), _ptr(_scratch(dev)), _stream(dev)), "rt_allhits_trace")
-        h = int(total.item())
-        loc = torch.empty((h, 3), dtype=torch.float32, device=dev)
-        ray_idx = torch.empty(h, dtype=torch.int32, device=dev)
-        tri_idx = torch.empty(h, dtype=torch.int32, device=dev)
-        if h > 0:
-            _check(lib.rt_allhits_scatter(n, max_hits, _ptr(counts), _ptr(staging), _ptr(ws), _ptr(loc), _ptr(ray_idx),
-                                          _ptr(tri_idx), _stream(dev)), "rt_allhits_scatter")
-    return loc, ray_idx, tri_idx
+        for first in range(ray_first, ray_first + n, per):
+            m = min(per, ray_first + n - first)
+            state, h = allhits_trace(accel_structure, origins, dirs, max_hits, first, m)
+            loc = torch.empty((h, 3), dtype=torch.float32, device=dev)
+            ray_idx = torch.empty(h, dtype=ray_idx_dtype, device=dev)
+            tri_idx = torch.empty(h, dtype=torch.int32, device=dev)
+            if h > 0:
+                allhits_scatter_at(state, ray_idx_base + first, rb, loc.data_ptr(), ray_idx.data_ptr(), tri_idx.data_ptr())
+            parts.append((loc, ray_idx, tri_idx))
+            del state
+        if not parts:
+            return (torch.empty((0, 3), dtype=torch.float32, device=dev), torch.empty(0, dtype=ray_idx_dtype, device=dev),
+                    torch.empty(0, dtype=torch.int32, device=dev))
+        if len(parts) == 1:
+            return parts[0]
+        return tuple(torch.cat([p[i] for p in parts], dim=0) for i in range(3))
 
 
-def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, aabb_hi):
+def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, aabb_hi, active: torch.Tensor | None = None,
+                    out=None):
     """Fused core of contains_points (reference ray_optix.py:238-267): returns
-    (contain Bool[*b], broken Bool[*b], flags Int32[2] = [any(inside_aabb), any(broken)])."""
+    (contain Bool[*b], broken Bool[*b], flags Int32[2] = [any(inside_aabb), any(broken)]).
+    With `active` (Bool[*b]) only the masked points are traced and written, in place into `out` = (contain, broken);
+    `active` may be the `broken` tensor itself (the retry of ray_optix.py:272-277 without gather / scatter)."""
     tensor_input_check(points)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, points.device)
     rd, batch = make_ray_desc(points, None)
     dev = points.device
     d3 = (C.c_float * 3)(*[float(x) for x in direction])
     lo3 = (C.c_float * 3)(*[float(x) for x in aabb_lo])
     hi3 = (C.c_float * 3)(*[float(x) for x in aabb_hi])
     with torch.cuda.device(dev):
-        contain = torch.empty(batch, dtype=torch.bool, device=dev)
-        broken = torch.empty(batch, dtype=torch.bool, device=dev)
+        if out is None:
+            if active is not None:
+                raise ValueError("contains_parity: a masked call updates existing (contain, broken) tensors: pass out=")
+            contain = torch.empty(batch, dtype=torch.bool, device=dev)
+            broken = torch.empty(batch, dtype=torch.bool, device=dev)
+        else:
+            contain, broken = out
+            for t in (contain, broken) + ((active,) if active is not None else ()):
+                if t.dtype != torch.bool or t.device != dev or not t.is_contiguous() or t.numel() != rd.nray:
+                    raise ValueError("contains_parity: masks must be contiguous bool tensors over the point batch")
         flags = torch.empty(2, dtype=torch.int32, device=dev)
-        _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), d3, lo3, hi3, _ptr(contain), _ptr(broken),
-                                               _ptr(flags), _ptr(_scratch(dev)), _stream(dev)), "rt_contains_parity")
+        _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), d3, lo3, hi3,
+                                               _ptr(active), _ptr(contain), _ptr(broken), _ptr(flags), _ptr(_scratch(dev)),
+                                               _stream(dev)), "rt_contains_parity")
     return contain, broken, flags
 
 
 def trace_stats(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, mode: str = "closest") -> dict:
     """Instrumented traversal: mean BVH8 nodes / triangles fetched per ray (roofline input)."""
     tensor_input_check(origins, dirs)
-    blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
+    blob = _blob_of(accel_structure, origins.device)
     rd, _ = make_ray_desc(origins, dirs)
     dev = origins.device
     with torch.cuda.device(dev):
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
-        _check(get_module().rt_trace_stats(_ptr(blob), C.byref(rd), {"closest": 0, "any": 1, "count": 2}[mode],
-                                           _ptr(counters), _ptr(_scratch(dev)), _stream(dev)), "rt_trace_stats")
+        _check(get_module().rt_trace_stats(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)),
+                                           {"closest": 0, "any": 1, "count": 2}[mode], _ptr(counters), _ptr(_scratch(dev)),
+                                           _stream(dev)), "rt_trace_stats")
         c = counters.cpu().tolist()
     rays = max(c[2], 1)
     return dict(nodes=c[0], tris=c[1], rays=c[2], hits=c[3], nodes_per_ray=c[0] / rays, tris_per_ray=c[1] / rays,
@@ -599,13 +716,15 @@ def trace_stats(accel_structure, origins: torch.Tensor, dirs: torch.Tensor, mode
 
 
 def host_closest(accel_structure, origins_host: torch.Tensor, dirs_host: torch.Tensor, out: dict | None = None,
-                 work: torch.Tensor | None = None):
+                 work: torch.Tensor | None = None, stream_compaction: bool = False):
     """End-to-end closest hit with HOST (ideally pinned) buffers: rt_host_trace_closest pipelines
     H2D copy, traversal and D2H copy over ray chunks.  origins_host may be [n,3] or a single
-    [3]/[1,3] origin shared by all rays.  Returns a dict of host tensors."""
+    [3]/[1,3] origin shared by all rays.  Returns a dict of host tensors (dense 5-tuple fields).
+    stream_compaction=True (rt_host_trace_closest_compact) compacts on the device and copies back only the hit
+    mask and the packed rows: the dict then holds hit[*b], n_hit and front / ray_idx / tri / loc / uv whose first
+    n_hit rows are valid (views `*_c` are added for convenience)."""
     lib = get_module()
     blob = _blob_of(accel_structure)
-    _apply_tmax(accel_structure)
     dev = blob.device
     d = dirs_host
     if d.is_cuda or d.dtype != torch.float32 or not d.is_contiguous() or d.shape[-1] != 3:
@@ -618,24 +737,44 @@ def host_closest(accel_structure, origins_host: torch.Tensor, dirs_host: torch.T
     if not bcast and o.numel() != 3 * n:
         raise ValueError("origins_host must hold 3 or 3*nray floats")
     batch = tuple(d.shape[:-1])
+    if work is None and out is not None:
+        work = out.get("_work")
     if out is None:
         pin = torch.cuda.is_available()
+        rows = (n,) if stream_compaction else batch
         out = dict(hit=torch.empty(batch, dtype=torch.bool, pin_memory=pin),
-                   front=torch.empty(batch, dtype=torch.bool, pin_memory=pin),
-                   tri=torch.empty(batch, dtype=torch.int32, pin_memory=pin),
-                   loc=torch.empty((*batch, 3), dtype=torch.float32, pin_memory=pin),
-                   uv=torch.empty((*batch, 2), dtype=torch.float32, pin_memory=pin))
+                   front=torch.empty(rows, dtype=torch.bool, pin_memory=pin),
+                   tri=torch.empty(rows, dtype=torch.int32, pin_memory=pin),
+                   loc=torch.empty((*rows, 3), dtype=torch.float32, pin_memory=pin),
+                   uv=torch.empty((*rows, 2), dtype=torch.float32, pin_memory=pin))
+        if stream_compaction:
+            out["ray_idx"] = torch.empty(rows, dtype=torch.int32, pin_memory=pin)
     with torch.cuda.device(dev):
         wb = C.c_size_t()
         _check(lib.rt_host_closest_sizes(n, C.byref(wb)), "rt_host_closest_sizes")
         if work is None or work.numel() < wb.value:
             work = torch.empty(wb.value, dtype=torch.uint8, device=dev)
         torch.cuda.current_stream(dev).synchronize()   # blob must be complete before the private streams read it
-        _check(lib.rt_host_trace_closest(_ptr(blob), n, C.c_void_p(o.data_ptr()), bcast, C.c_void_p(d.data_ptr()),
-                                         C.c_void_p(out["hit"].data_ptr()), C.c_void_p(out["front"].data_ptr()),
-                                         C.c_void_p(out["tri"].data_ptr()), C.c_void_p(out["loc"].data_ptr()),
-                                         C.c_void_p(out["uv"].data_ptr()), _ptr(work), work.numel()),
-               "rt_host_trace_closest")
+        opts = trace_opts(accel_structure)
+        if stream_compaction:
+            nh = C.c_int64(0)
+            _check(lib.rt_host_trace_closest_compact(_ptr(blob), n, C.c_void_p(o.data_ptr()), bcast, C.c_void_p(d.data_ptr()),
+                                                     C.byref(opts), C.c_void_p(out["hit"].data_ptr()),
+                                                     C.c_void_p(out["front"].data_ptr()), C.c_void_p(out["ray_idx"].data_ptr()),
+                                                     C.c_void_p(out["tri"].data_ptr()), C.c_void_p(out["loc"].data_ptr()),
+                                                     C.c_void_p(out["uv"].data_ptr()), C.byref(nh), _ptr(work), work.numel()),
+                   "rt_host_trace_closest_compact")
+            h = int(nh.value)
+            out["n_hit"] = h
+            for k in ("front", "ray_idx", "tri", "loc", "uv"):
+                out[k + "_c"] = out[k][:h]
+        else:
+            _check(lib.rt_host_trace_closest(_ptr(blob), n, C.c_void_p(o.data_ptr()), bcast, C.c_void_p(d.data_ptr()),
+                                             C.byref(opts), C.c_void_p(out["hit"].data_ptr()),
+                                             C.c_void_p(out["front"].data_ptr()), C.c_void_p(out["tri"].data_ptr()),
+                                             C.c_void_p(out["loc"].data_ptr()), C.c_void_p(out["uv"].data_ptr()), _ptr(work),
+                                             work.numel()), "rt_host_trace_closest")
+    out["_work"] = work
     return out
 
 

@@ -327,16 +327,18 @@ class ShardedRayMeshIntersector:
         from triro.backend import ops as hops
 
         batch = tuple(origins.shape[:-1])
-        n, lo, hi, o, d = self._slice(origins, directions)
+        n = origins.numel() // 3
+        lo, hi = shard_bounds(n, self.world, self.rank)      # the slice is a ray WINDOW of the full batch: no copy
         if outputs is None or outputs.nray != n:
-            outputs = PeerOutputs(n, o.device, self.group)
+            outputs = PeerOutputs(n, origins.device, self.group)
         if kernel_stores is None:
             kernel_stores = self.world <= 2
         if hi > lo:
             if kernel_stores:
-                hops.intersects_closest_into(self.local.as_wrapper, o, d, *outputs.addresses(root, lo))
+                hops.intersects_closest_into(self.local.as_wrapper, origins, directions, *outputs.addresses(root, lo),
+                                             ray_first=lo, ray_count=hi - lo)
             else:     # trace into local tensors, then five bulk peer-to-peer copies
-                res = hops.intersects_closest(self.local.as_wrapper, o, d)
+                res = hops.intersects_closest(self.local.as_wrapper, origins, directions, lo, hi - lo)
                 for dst, src in zip(outputs.peer_slices(root, lo, hi), res):
                     dst.copy_(src.reshape(-1).view(dst.dtype) if src.dtype == torch.bool else src.reshape(-1))
         torch.cuda.current_stream().synchronize()      # this rank's stores have left; then everybody's have
@@ -362,9 +364,10 @@ class ShardedRayMeshIntersector:
         from triro.backend import ops as hops
 
         batch = tuple(origins.shape[:-1])
-        n, lo, hi, o, d = self._slice(origins, directions)
-        dev = o.device
-        hit, front, tri, loc, uv = hops.intersects_closest(self.local.as_wrapper, o, d)
+        n = origins.numel() // 3
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        dev = origins.device
+        hit, front, tri, loc, uv = hops.intersects_closest(self.local.as_wrapper, origins, directions, lo, hi - lo)
         ws, total = hops.compact_scan(hit)
         rb = 8 if n > 2**31 - 1 else 4
         mine = None
@@ -401,15 +404,15 @@ class ShardedRayMeshIntersector:
         (loc[h,3], ray_idx[h], tri_idx[h]) on `root`, None elsewhere."""
         from triro.backend import ops as hops
 
-        n, lo, hi, o, d = self._slice(origins, directions)
-        dev = o.device
-        state, total = hops.allhits_trace(self.local.as_wrapper, o, d, getattr(self.local, "max_hits", 8))
+        n = origins.numel() // 3
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        dev = origins.device
         rb = 8 if n > 2**31 - 1 else 4
-        mine = dict(loc=torch.empty(3 * total, dtype=torch.float32, device=dev),
-                    ray=torch.empty(total, dtype=torch.int64 if rb == 8 else torch.int32, device=dev),
-                    tri=torch.empty(total, dtype=torch.int32, device=dev))
-        if total > 0:
-            hops.allhits_scatter_at(state, lo, rb, mine["loc"].data_ptr(), mine["ray"].data_ptr(), mine["tri"].data_ptr())
+        # this rank's window of the batch, traced in bounded staging windows; ray indices are global already
+        loc, ray, tri = hops.intersects_location(self.local.as_wrapper, origins, directions, getattr(self.local, "max_hits", 8),
+                                                 0, torch.int64 if rb == 8 else torch.int32, None, lo, hi - lo)
+        total = int(tri.shape[0])
+        mine = dict(loc=loc.reshape(-1), ray=ray, tri=tri)
         counts = all_counts(total, dev, self.group)
         hits, row0 = sum(counts), sum(counts[: self.rank])
         packed = self._packed_for(packed, hits, n, dev)
@@ -435,17 +438,39 @@ class ShardedRayMeshIntersector:
 
     def intersects_id(self, origins, directions, return_locations: bool = False, multiple_hits: bool = True,
                       gather: bool = True):
+        """(tri_idx, ray_idx[, loc]) like RayMeshIntersector.intersects_id; with gather=False this rank's part (ray
+        indices in the global numbering) plus its slice bounds."""
         if multiple_hits:
-            loc, ray_idx, tri_idx = self.intersects_location(origins, directions, gather=True)
+            res = self.intersects_location(origins, directions, gather=gather)
+            (loc, ray_idx, tri_idx), bounds = res if not gather else (res, None)
         else:
-            _, _, ray_idx, tri_idx, loc, _ = self.intersects_closest(origins, directions, stream_compaction=True, gather=True)
-        return (tri_idx, ray_idx, loc) if return_locations else (tri_idx, ray_idx)
+            res = self.intersects_closest(origins, directions, stream_compaction=True, gather=gather)
+            (_, _, ray_idx, tri_idx, loc, _), bounds = res if not gather else (res, None)
+        out = (tri_idx, ray_idx, loc) if return_locations else (tri_idx, ray_idx)
+        return out if gather else (out, bounds)
 
     def contains_points(self, points, check_direction=None, gather: bool = True):
+        """`contains_points` of the full point batch, sharded.  The two decisions the reference takes on the WHOLE
+        batch (any point inside the AABB? any point broken?, ray_optix.py:243,269) are OR-reduced over the ranks and
+        the random retry direction is drawn on rank 0 and broadcast, so N ranks return what one process returns -
+        including the reference's all-False quirk branches."""
+        from triro.ray.ray_optix import contains_points_flow
+
         n = points.numel() // 3
         lo, hi = shard_bounds(n, self.world, self.rank)
         p = points.reshape(-1, 3)[lo:hi]
-        res = self.local.contains_points(p, check_direction)
+
+        def reduce_flags(flags):
+            f = flags.to(torch.int32).clone()
+            dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+            return tuple(int(x) for x in f.tolist())
+
+        def draw_direction():
+            d = (torch.rand(3) - 0.5).to(p.device) if self.rank == 0 else torch.empty(3, device=p.device)
+            dist.broadcast(d, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            return d.tolist()
+
+        res = contains_points_flow(self.local.contains_parity, p, check_direction, reduce_flags, draw_direction)
         if not gather:
             return res, (lo, hi)
         return gather_fixed(res, self._counts(n), self.group).reshape(points.shape[:-1])

@@ -24,8 +24,9 @@ class RayMeshIntersector:
         if vertices is None or faces is None:
             raise ValueError("a mesh or vertices and faces must be provided")
         self.device = torch.device(device)
-        self._rmi = _TorchIntersector(vertices=torch.as_tensor(np.asarray(vertices, dtype=np.float32)),
-                                      faces=torch.as_tensor(np.asarray(faces).astype(np.int32)))
+        # mesh, BVH and rays all live on `device` (the intersector keeps a CUDA input's device)
+        self._rmi = _TorchIntersector(vertices=torch.as_tensor(np.asarray(vertices, dtype=np.float32)).to(self.device),
+                                      faces=torch.as_tensor(np.asarray(faces).astype(np.int32)).to(self.device))
 
     def _rays(self, ray_origins, ray_directions):
         o = np.asarray(ray_origins, dtype=np.float32).reshape(-1, 3)

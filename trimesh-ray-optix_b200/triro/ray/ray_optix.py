@@ -46,9 +46,12 @@ class RayMeshIntersector:
 
     def update_raw(self, vertices: torch.Tensor, faces: torch.Tensor):
         """Replace the mesh and rebuild the acceleration structure (reference ray_optix.py:55-69)."""
-        # [n, 3] float32 / [f, 3] int32 on the device
-        self.mesh_vertices = vertices.float().contiguous().cuda()
-        self.mesh_faces = faces.int().contiguous().cuda()
+        # [n, 3] float32 / [f, 3] int32 on the device: a CUDA input keeps its device, a host input goes to the
+        # current one (the reference's `.cuda()`, ray_optix.py:57-58); both must end up on the same device
+        self.mesh_vertices = vertices.float().contiguous()
+        if not self.mesh_vertices.is_cuda:
+            self.mesh_vertices = self.mesh_vertices.cuda()
+        self.mesh_faces = faces.int().contiguous().to(self.mesh_vertices.device)
         if self.mesh_vertices.shape[0] > 0:
             self.mesh_aabb = (
                 torch.min(self.mesh_vertices, dim=0)[0],
@@ -64,7 +67,7 @@ class RayMeshIntersector:
         """Extension: move the vertices of the SAME topology and re-fit the BVH in place
         instead of rebuilding it (`update_raw`, like the reference, always rebuilds).  Results are
         exact for the deformed mesh; traversal efficiency degrades if the deformation is large."""
-        self.mesh_vertices = vertices.float().contiguous().cuda()
+        self.mesh_vertices = vertices.float().contiguous().to(self.as_wrapper.blob.device)
         self.mesh_aabb = (torch.min(self.mesh_vertices, dim=0)[0], torch.max(self.mesh_vertices, dim=0)[0])
         self._aabb_host = (self.mesh_aabb[0].tolist(), self.mesh_aabb[1].tolist())
         self.as_wrapper._inner.refit(self.mesh_vertices, self.mesh_faces)
@@ -139,6 +142,11 @@ class RayMeshIntersector:
 
     DEFAULT_CHECK_DIRECTION = (0.4395064455, 0.617598629942, 0.652231566745)   # reference :245-247
 
+    def contains_parity(self, points: torch.Tensor, direction, active: Optional[torch.Tensor] = None, out=None):
+        """Fused core of `contains_points`: (contain, broken, flags[2] = [any inside the AABB, any broken]) for one
+        direction; with `active` / `out` a masked in-place update (see hops.contains_parity)."""
+        return hops.contains_parity(self.as_wrapper, points, direction, self._aabb_host[0], self._aabb_host[1], active, out)
+
     def contains_points(self, points: torch.Tensor, check_direction: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Bool[n] — is each point inside the (closed) mesh (reference :231-279).
 
@@ -149,21 +157,39 @@ class RayMeshIntersector:
         broken the reference returns its initial all-False tensor (:279) — kept.
         The two count traversals, the AABB test and the parity logic run in one kernel.
         """
-        contain, broken, flags = hops.contains_parity(
-            self.as_wrapper, points,
-            self.DEFAULT_CHECK_DIRECTION if check_direction is None else check_direction.detach().flatten().tolist(),
-            self._aabb_host[0], self._aabb_host[1])
-        any_inside, any_broken = (int(x) for x in flags.tolist())     # one host sync for both decisions
-        if not any_inside:                                            # reference :243-244
-            return torch.zeros(points.shape[:-1], dtype=torch.bool, device=points.device)
-        if not any_broken:                                            # reference :269-270
-            return contain
-        if check_direction is None:                                   # reference :272-277
-            new_direction = (torch.rand(3) - 0.5).cuda()
-            contains = contain
-            contains[broken] = self.contains_points(points[broken], new_direction)
-            return contains
-        return torch.zeros(points.shape[:-1], dtype=torch.bool, device=points.device)   # reference :236,:279
+        return contains_points_flow(self.contains_parity, points, check_direction)
+
+
+def contains_points_flow(parity, points: torch.Tensor, check_direction, reduce_flags=None, draw_direction=None):
+    """Control flow of the reference's `contains_points` (ray_optix.py:236-279) around the fused parity kernel.
+
+    `parity(points, direction, active, out)` is RayMeshIntersector.contains_parity.  A ray-sharded caller
+    (triro.distributed) passes `reduce_flags` (OR of the two decision flags over all ranks) and `draw_direction`
+    (one retry direction for all ranks), so that N ranks take the branches one process would take."""
+    zeros = lambda: torch.zeros(points.shape[:-1], dtype=torch.bool, device=points.device)   # noqa: E731  (:236)
+    read = reduce_flags if reduce_flags is not None else (lambda f: tuple(int(x) for x in f.tolist()))
+    direction = (RayMeshIntersector.DEFAULT_CHECK_DIRECTION if check_direction is None
+                 else check_direction.detach().flatten().tolist())
+    contain, broken, flags = parity(points, direction, None, None)
+    any_inside, any_broken = read(flags)                              # one host sync for both decisions
+    if not any_inside:                                                # reference :243-244
+        return zeros()
+    if not any_broken:                                                # reference :269-270
+        return contain
+    if check_direction is not None:                                   # reference :236,:279
+        return zeros()
+    # reference :272-277: contains[broken] = self.contains_points(points[broken], new_direction) — as ONE masked,
+    # in-place launch: only the broken points are traced again and only their entries are rewritten (no
+    # points[broken] gather, no boolean-index scatter).  The recursive call's own early returns are kept: it
+    # yields all False for the subset when none of the broken points lies inside the AABB (:243-244) or when
+    # some point is broken again (a direction was given, :279); otherwise the subset's parity result.
+    new_direction = draw_direction() if draw_direction is not None else (torch.rand(3) - 0.5).tolist()   # CPU generator, as :273
+    was_broken = broken.clone()
+    _, _, flags = parity(points, new_direction, broken, (contain, broken))
+    sub_inside, sub_broken = read(flags)
+    if not sub_inside or sub_broken:
+        contain[was_broken] = False
+    return contain
 
 
 class OptixAccelStructureWrapper:
