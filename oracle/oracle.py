@@ -54,11 +54,18 @@ def lib():
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 8 + \
                                      [C.c_int] + [C.c_void_p] * 4
         _LIB.oracle_num_threads.restype = C.c_int
+        _LIB.oracle_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of later query() calls (bench.py: all host cores, whatever OMP_NUM_THREADS a launcher set)."""
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
 
 
 def _p(a):

@@ -553,3 +553,13 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Worker threads of the following oracle_query calls.  bench.py's CPU legs use it to take every host core even when
+ * a launcher (torch.distributed.run) exported OMP_NUM_THREADS=1 into the process. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

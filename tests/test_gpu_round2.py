@@ -121,11 +121,22 @@ def test_allhits_in_bounded_staging_windows_equals_one_launch(cuda_device):
     one = hops.intersects_location(r.as_wrapper, o, d, 8)
     many = hops.intersects_location(r.as_wrapper, o, d, 8, staging_bytes=3000 * 8 * 16)      # 14 windows
     assert one[1].shape[0] > 10_000
-    for a, b in zip(one, many):
-        assert torch.equal(a, b)
+
+    few = (r.intersects_count(o, d) <= 8).cpu().numpy()       # with more than 8 hits WHICH 8 are kept is unspecified (as in the reference)
+
+    def canon(res):        # hits of one ray come in traversal order, which depends on what shares its warp: sort within the ray
+        loc, ri, ti = (x.cpu().numpy() for x in res)
+        keep = few[ri]
+        loc, ri, ti = loc[keep], ri[keep], ti[keep]
+        order = np.lexsort((ti, ri))
+        return ri[order], ti[order], loc[order].view(np.uint32)
+
+    assert torch.equal(one[1], many[1]) and bool((one[1][1:] >= one[1][:-1]).all())     # same rays, ascending
+    for a, b in zip(canon(one), canon(many)):
+        assert np.array_equal(a, b)
     assert hops.allhits_window_rays(8) * 8 * 16 <= hops.ALLHITS_STAGING_BYTES
-    # what a 100 M-ray config-3 call allocates at a time: <= 1 GiB instead of 12.8 GB
-    assert hops.allhits_window_rays(8) == (1 << 30) // 128
+    # what a 100 M-ray config-3 call allocates at a time: <= 2 GiB instead of 12.8 GB
+    assert hops.allhits_window_rays(8) == (2 << 30) // 128
 
 
 # ---------------------------------------------------------------- contains_points

@@ -152,6 +152,7 @@ struct VisitorOf {
 // A warp re-fills its finished lanes from the global ray counter as soon as fewer than
 // `refill_threshold` lanes are still busy (defaults below; TRIRO_REFILL_THRESHOLD overrides).
 constexpr int kRefillThresholdQueued = 28;
+constexpr int kRefillThresholdCoopIncoherent = 24;   // measured: 24 beats 28 by 1-2 % on the heightfields (profiles/r2_sweeps.md)
 constexpr int kRefillThresholdDirect = 8;
 // Postponed triangle tests: every lane owns a queue of pending triangle record indices in shared
 // memory (s_queue[entry][thread], conflict-free).  Node steps only enqueue; a warp runs a triangle
@@ -179,6 +180,9 @@ struct LaneQueue {
 // lanes reach their leaves in the same step anyway, and the nearest hit shrinks tmax earlier).
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 7
+#endif
+#ifndef RT_TRACE_MIN_BLOCKS_LIGHT      // cooperative kernels other than pooled closest-hit: 64 registers, 8 CTAs per SM
+#define RT_TRACE_MIN_BLOCKS_LIGHT 8
 #endif
 template <int MODE, bool STATS, bool QUEUED>
 __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ TraceParams p) {
@@ -583,7 +587,8 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     const bool coop = sched >= RT_SCHED_COOP_COHERENT;
     auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
     p.refill_threshold = o.refill_threshold > 0 ? clampi(o.refill_threshold, 1, 32)
-                                                : (early ? kRefillThresholdQueued : kRefillThresholdDirect);
+                                                : (sched == RT_SCHED_COOP_INCOHERENT ? kRefillThresholdCoopIncoherent
+                                                   : (early ? kRefillThresholdQueued : kRefillThresholdDirect));
     p.tri_threshold = o.tri_threshold > 0 ? clampi(o.tri_threshold, 1, coop ? kPairCap - 32 : 32)
                                           : (coop ? (early ? kPairThresholdIncoherent : kPairThresholdCoherent) : kTriThreshold);
     RT_REQUIRE(dev.device >= 0 && dev.device < kMaxDevices, RT_ERR_CUDA, "%s: device index %d not supported", fn, dev.device);

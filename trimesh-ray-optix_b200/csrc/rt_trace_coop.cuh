@@ -31,15 +31,15 @@ constexpr int kRayWords = 7;           // resident part of a ray in shared memor
 // POOL = incoherent batches: rays are prepared 32 at a time into a shared-memory pool and lanes re-fill early;
 // otherwise lanes re-fill late and set their ray up in place (coherent batches).
 template <int MODE, bool STATS, bool POOL>
-__global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_coop(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(kTraceThreads, (MODE == kClosest && POOL) ? RT_TRACE_MIN_BLOCKS : RT_TRACE_MIN_BLOCKS_LIGHT)
+k_trace_coop(const __grid_constant__ TraceParams p) {
     static_assert(MODE != kAllHits, "all-hits keeps the per-lane schedule (deterministic record order)");
     constexpr bool kKey = MODE == kClosest || MODE == kFirst;
     __shared__ float s_ray[kRayWords][kTraceThreads];
     __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim
     __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
     __shared__ float s_attr[MODE == kClosest ? 6 : 1][kTraceThreads];    // loc(3), uv(2), front
-    __shared__ uint32_t s_pair[kTraceThreads / 32][kPairCap];
-    __shared__ uint8_t s_plane[kTraceThreads / 32][kPairCap];
+    __shared__ uint2 s_pair[kTraceThreads / 32][kPairCap];               // (triangle record, owner lane)
     __shared__ float s_pool[POOL ? kPoolWords : 1][kTraceThreads];
     init_mask_luts();
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_co
     int phase = 0;
     uint32_t count_plus = 0;
     int n_pend = 0;                   // pairs in the warp's list (warp-uniform)
-    int my_pend = 0;                  // of which belong to this lane's ray
+    int my_pend = 0;                  // != 0: some of them belong to this lane's ray
     int pool_head = 0, pool_count = 0;
     int64_t pool_base = 0;
     uint32_t ty = 0u, tx = 0u, tmask = 0u;      // triangles of this lane's last node step not yet listed
@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_co
             Ray t;
             float v0x = 0, v0y = 0, v0z = 0, v1x = 0, v1y = 0, v1z = 0, v2x = 0, v2y = 0, v2z = 0;
             if (i < n_pend) {
-                const uint32_t slot = s_pair[warp][i];
-                col = col0 + (int)s_plane[warp][i];
+                const uint2 pr = s_pair[warp][i];
+                const uint32_t slot = pr.x;
+                col = col0 + (int)pr.y;
                 t.Sx = s_ray[0][col]; t.Sy = s_ray[1][col]; t.Sz = s_ray[2][col];
                 t.okx = s_ray[3][col]; t.oky = s_ray[4][col]; t.okz = s_ray[5][col];
                 t.kzf = __float_as_int(s_ray[6][col]);
@@ -135,10 +136,12 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_co
         const unsigned done_mask = __ballot_sync(0xffffffffu, !active || nodes_done);
         const int busy = 32 - __popc(done_mask);
         const bool want_refill = done_mask != 0u && busy < ((exhausted && pool_count == 0) ? 1 : p.refill_threshold);
-        const unsigned unlisted = __ballot_sync(0xffffffffu, ty != 0u);
-        if (n_pend > 0 && (n_pend >= p.tri_threshold || (unlisted != 0u && n_pend + 32 > kPairCap) ||
-                           (want_refill && __any_sync(0xffffffffu, active && nodes_done && my_pend > 0))))
-            flush();
+        if (n_pend > 0) {
+            bool go = n_pend >= p.tri_threshold;
+            if (!go && n_pend == kPairCap) go = true;                                                      // list full (triangles may be waiting in ty)
+            if (!go && want_refill) go = __any_sync(0xffffffffu, active && nodes_done && my_pend != 0);   // rays wait to retire
+            if (go) flush();
+        }
         if (want_refill) {
             if (active && nodes_done && my_pend == 0 && ty == 0u) {
                 if constexpr (MODE == kClosest || MODE == kFirst) {
@@ -299,20 +302,27 @@ __global__ void __launch_bounds__(kTraceThreads, RT_TRACE_MIN_BLOCKS) k_trace_co
             }
         }
 
-        // ---- 3. append (lane, triangle) pairs to the warp's list, one per lane and round; what does not fit
-        //         stays in ty and is listed after the next flush (such a lane takes no node step meanwhile)
-        unsigned has = __ballot_sync(0xffffffffu, ty != 0u);
-        while (has != 0u && n_pend + 32 <= kPairCap) {
-            if (ty != 0u) {
+        // ---- 3. append this step's (triangle, lane) pairs to the warp's list: one warp scan of the per-lane counts gives
+        //         every lane its first position; what does not fit stays in ty and is listed after the next flush (such a
+        //         lane takes no node step meanwhile)
+        if (__any_sync(0xffffffffu, ty != 0u)) {
+            const int c = __popc(ty);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int pos = n_pend + incl - c;
+            if (ty != 0u && pos < kPairCap) my_pend = 1;
+            while (ty != 0u && pos < kPairCap) {
                 const int b = ffs32(ty) - 1;
                 ty &= ty - 1u;
-                const int pos = n_pend + __popc(has & lt_mask);
-                s_pair[warp][pos] = tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b));
-                s_plane[warp][pos] = (uint8_t)lane;
-                ++my_pend;
+                s_pair[warp][pos] = make_uint2(tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b)), (uint32_t)lane);
+                ++pos;
             }
-            n_pend += __popc(has);
-            has = __ballot_sync(0xffffffffu, ty != 0u);
+            n_pend = n_pend + total < kPairCap ? n_pend + total : kPairCap;
         }
     }
     if (MODE == kContains) {

@@ -41,17 +41,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every translation unit (in parallel) and link the shared library."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, extra: list[str] | None = None) -> str:
+    """Compile every translation unit (in parallel) and link the shared library.
+    `variant` + `extra` nvcc flags build an experiment library next to it (libtriro_b200_<variant>.so, selected with
+    TRIRO_B200_LIB); the product is the plain build."""
+    lib_path = LIB_PATH if variant is None else os.path.join(HERE, f"libtriro_b200_{variant}.so")
+    if variant is None and not force and not is_stale():
         return LIB_PATH
     nvcc = nvcc_path()
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" if variant is None else f"build_{variant}")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(unit: str) -> str:
         obj = os.path.join(objdir, unit.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("TRIRO_NVCC_EXTRA", "").split(), "-I", INCLUDE, "-c",
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("TRIRO_NVCC_EXTRA", "").split(), *(extra or []), "-I", INCLUDE, "-c",
                os.path.join(CSRC, unit), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -64,15 +67,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     r = subprocess.run([nvcc, *ARCH, "-shared", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var[0] if var else None,
+                extra=[a for a in sys.argv[1:] if a.startswith("-D")]))

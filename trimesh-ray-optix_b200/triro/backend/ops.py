@@ -28,7 +28,7 @@ BLOB_MAGIC = 0x38485642
 MAX_DEPTH = 60               # rt_core.cuh kMaxDepth
 HOST_CHUNK = 1 << 20
 ABI_VERSION = 2
-ALLHITS_STAGING_BYTES = 1 << 30   # all-hits staging per launch window (nray_window * max_hits * 16 B)
+ALLHITS_STAGING_BYTES = 2 << 30   # all-hits staging per launch window (nray_window * max_hits * 16 B)
 
 _lib = None
 
