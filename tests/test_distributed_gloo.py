@@ -46,7 +46,7 @@ class OracleBackedLocal:
     def contains_points(self, p, check_direction=None):
         return self._t(self.oi.contains_points(p.numpy(), check_direction))
 
-    def contains_parity(self, points, direction, active=None, out=None):
+    def contains_parity(self, points, direction, active=None, out=None, stop_when_broken=False):
         """Stand-in for RayMeshIntersector.contains_parity (the fused kernel): same outputs, masked in-place update."""
         inside, cp, cm = self.oi.contains_core(points.numpy(), direction)
         agree = (cp % 2 == 1) & (cm % 2 == 1)

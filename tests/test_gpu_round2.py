@@ -17,7 +17,7 @@ from triro.ray.ray_optix import RayMeshIntersector
 pytestmark = pytest.mark.gpu
 
 SCHEDULES = {"direct": hops.SCHED_DIRECT, "queued": hops.SCHED_QUEUED, "coop_coherent": hops.SCHED_COOP_COHERENT,
-             "coop_incoherent": hops.SCHED_COOP_INCOHERENT}
+             "coop_incoherent": hops.SCHED_COOP_INCOHERENT, "slots": hops.SCHED_SLOTS}
 
 
 def make(v, f, **kw):

@@ -45,6 +45,7 @@ struct TraceParams {
     // contains
     float dir[3], aabb_lo[3], aabb_hi[3];
     const uint8_t* active;       // optional per-point mask (may alias `broken`)
+    int stop_on_broken;          // RT_OPT_STOP_WHEN_BROKEN
     uint8_t* contain;
     uint8_t* broken;
     int32_t* flags;
@@ -152,6 +153,7 @@ struct VisitorOf {
 // A warp re-fills its finished lanes from the global ray counter as soon as fewer than
 // `refill_threshold` lanes are still busy (defaults below; TRIRO_REFILL_THRESHOLD overrides).
 constexpr int kRefillThresholdQueued = 28;
+constexpr int kRefillThresholdSlots = 29;             // slot schedule: a lane adopts a prepared ray as soon as 4 lanes are idle
 constexpr int kRefillThresholdCoopIncoherent = 24;   // measured: 24 beats 28 by 1-2 % on the heightfields (profiles/r2_sweeps.md)
 constexpr int kRefillThresholdDirect = 8;
 // Postponed triangle tests: every lane owns a queue of pending triangle record indices in shared
@@ -485,6 +487,7 @@ __device__ __forceinline__ void release_scratch(const TraceParams& p) {
 
 }  // namespace rt
 #include "rt_trace_coop.cuh"
+#include "rt_trace_slots.cuh"
 namespace rt {
 
 static int fetch_mode(const int64_t shape[4], const int64_t stride[4], int64_t nray);
@@ -525,13 +528,20 @@ static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
 
 // resident CTAs per SM of every kernel variant, per device (filled on first use; benign race: same value)
 constexpr int kMaxDevices = 64;
-static int g_per_sm[kMaxDevices][4][2][8];
+static int g_per_sm[kMaxDevices][5][2][8];
+
+template <int MODE>
+constexpr bool kHasSlots = MODE == kClosest || MODE == kFirst || MODE == kAny || MODE == kCount;
 
 template <int MODE, bool STATS>
 static int occupancy(int sched, int* per_sm) {
     switch (sched) {
         case RT_SCHED_DIRECT: return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace<MODE, STATS, false>, kTraceThreads, 0);
         case RT_SCHED_QUEUED: return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace<MODE, STATS, true>, kTraceThreads, 0);
+        case RT_SCHED_SLOTS:
+            if constexpr (kHasSlots<MODE>)
+                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_slots<MODE, STATS>, kTraceThreads, 0);
+            return (int)cudaErrorInvalidValue;
         default:
             if constexpr (MODE != kAllHits) {
                 if (sched == RT_SCHED_COOP_COHERENT)
@@ -571,6 +581,7 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
         p.d_mode = MODE != kContains ? fetch_mode(rays->shape, rays->d_stride, rays->nray) : kConstant;
     }
     p.tmax = o.tmax > 0.0f ? o.tmax : RT_TMAX_DEFAULT;     // NaN and <= 0 select the reference's 1e7
+    p.stop_on_broken = (MODE == kContains && (o.flags & RT_OPT_STOP_WHEN_BROKEN)) ? 1 : 0;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
     if (!(o.flags & RT_OPT_SCRATCH_ZEROED)) RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
@@ -580,14 +591,15 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     // the warp-cooperative triangle tests of rt_trace_coop.cuh; all-hits keeps the per-lane queues.
     const bool coherent = MODE != kContains && (p.o_mode == kConstant || pinhole);
     int sched = o.schedule;
-    RT_REQUIRE(sched >= RT_SCHED_AUTO && sched <= RT_SCHED_COOP_INCOHERENT, RT_ERR_INVALID, "%s: unknown schedule %d", fn, sched);
+    RT_REQUIRE(sched >= RT_SCHED_AUTO && sched <= RT_SCHED_SLOTS, RT_ERR_INVALID, "%s: unknown schedule %d", fn, sched);
     if (sched == RT_SCHED_AUTO) sched = coherent ? RT_SCHED_COOP_COHERENT : RT_SCHED_COOP_INCOHERENT;
+    if (sched == RT_SCHED_SLOTS && !kHasSlots<MODE>) sched = RT_SCHED_COOP_INCOHERENT;      // contains / all hits
     if (MODE == kAllHits && sched >= RT_SCHED_COOP_COHERENT) sched = sched == RT_SCHED_COOP_COHERENT ? RT_SCHED_DIRECT : RT_SCHED_QUEUED;
-    const bool early = sched == RT_SCHED_QUEUED || sched == RT_SCHED_COOP_INCOHERENT;
+    const bool early = sched == RT_SCHED_QUEUED || sched == RT_SCHED_COOP_INCOHERENT || sched == RT_SCHED_SLOTS;
     const bool coop = sched >= RT_SCHED_COOP_COHERENT;
     auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
     p.refill_threshold = o.refill_threshold > 0 ? clampi(o.refill_threshold, 1, 32)
-                                                : (sched == RT_SCHED_COOP_INCOHERENT ? kRefillThresholdCoopIncoherent
+                                                : (sched == RT_SCHED_SLOTS ? kRefillThresholdSlots : sched == RT_SCHED_COOP_INCOHERENT ? kRefillThresholdCoopIncoherent
                                                    : (early ? kRefillThresholdQueued : kRefillThresholdDirect));
     p.tri_threshold = o.tri_threshold > 0 ? clampi(o.tri_threshold, 1, coop ? kPairCap - 32 : 32)
                                           : (coop ? (early ? kPairThresholdIncoherent : kPairThresholdCoherent) : kTriThreshold);
@@ -606,6 +618,9 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     switch (sched) {
         case RT_SCHED_DIRECT: k_trace<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p); break;
         case RT_SCHED_QUEUED: k_trace<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p); break;
+        case RT_SCHED_SLOTS:
+            if constexpr (kHasSlots<MODE>) k_trace_slots<MODE, STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            break;
         default:
             if constexpr (MODE != kAllHits) {
                 if (sched == RT_SCHED_COOP_COHERENT) k_trace_coop<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);

@@ -25,7 +25,10 @@
 
 namespace rt {
 
-constexpr int kPairCap = 128;          // pairs a warp can hold; a node step of 32 lanes appends 32 per round
+#ifndef RT_PAIR_CAP
+#define RT_PAIR_CAP 128
+#endif
+constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
 constexpr int kRayWords = 7;           // resident part of a ray in shared memory: S(3), permuted origin(3), kzf
 
 // POOL = incoherent batches: rays are prepared 32 at a time into a shared-memory pool and lanes re-fill early;
@@ -143,6 +146,15 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
             if (go) flush();
         }
         if (want_refill) {
+            if constexpr (MODE == kContains) {
+                // RT_OPT_STOP_WHEN_BROKEN (the retry of ray_optix.py:272-277): once any point is broken again the caller
+                // discards the whole launch, so stop drawing points
+                if (p.stop_on_broken && !(exhausted && pool_count == 0)) {
+                    int f = 0;
+                    if (lane == 0) f = *reinterpret_cast<volatile int32_t*>(&p.flags[1]);
+                    if (__shfl_sync(0xffffffffu, f, 0)) { exhausted = true; pool_count = 0; }
+                }
+            }
             if (active && nodes_done && my_pend == 0 && ty == 0u) {
                 if constexpr (MODE == kClosest || MODE == kFirst) {
                     const unsigned long long best = s_best[mycol];
@@ -188,6 +200,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                         p.contain[r] = (inside && agree) ? 1 : 0;
                         p.broken[r] = brk ? 1 : 0;
                         any_inside |= inside;
+                        if (brk && !any_broken && p.stop_on_broken) atomicOr(&p.flags[1], 1);     // tell the other warps now
                         any_broken |= brk;
                         active = false;
                     }

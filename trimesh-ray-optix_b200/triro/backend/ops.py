@@ -54,8 +54,9 @@ class TraceOpts(C.Structure):
                 ("grid_div", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
-SCHED_AUTO, SCHED_DIRECT, SCHED_QUEUED, SCHED_COOP_COHERENT, SCHED_COOP_INCOHERENT = 0, 1, 2, 3, 4
+SCHED_AUTO, SCHED_DIRECT, SCHED_QUEUED, SCHED_COOP_COHERENT, SCHED_COOP_INCOHERENT, SCHED_SLOTS = 0, 1, 2, 3, 4, 5
 OPT_SCRATCH_ZEROED = 1
+OPT_STOP_WHEN_BROKEN = 2
 
 
 class Pinhole(C.Structure):
@@ -668,11 +669,12 @@ def intersects_location(accel_structure, origins: torch.Tensor, dirs: torch.Tens
 
 
 def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, aabb_hi, active: torch.Tensor | None = None,
-                    out=None):
+                    out=None, stop_when_broken: bool = False):
     """Fused core of contains_points (reference ray_optix.py:238-267): returns
     (contain Bool[*b], broken Bool[*b], flags Int32[2] = [any(inside_aabb), any(broken)]).
     With `active` (Bool[*b]) only the masked points are traced and written, in place into `out` = (contain, broken);
-    `active` may be the `broken` tensor itself (the retry of ray_optix.py:272-277 without gather / scatter)."""
+    `active` may be the `broken` tensor itself (the retry of ray_optix.py:272-277 without gather / scatter).
+    `stop_when_broken`: the launch may end as soon as flags[1] is known to be 1 (per-point results unspecified then)."""
     tensor_input_check(points)
     blob = _blob_of(accel_structure, points.device)
     rd, batch = make_ray_desc(points, None)
@@ -692,7 +694,10 @@ def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, a
                 if t.dtype != torch.bool or t.device != dev or not t.is_contiguous() or t.numel() != rd.nray:
                     raise ValueError("contains_parity: masks must be contiguous bool tensors over the point batch")
         flags = torch.empty(2, dtype=torch.int32, device=dev)
-        _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), d3, lo3, hi3,
+        opts = trace_opts(accel_structure)
+        if stop_when_broken:
+            opts.flags |= OPT_STOP_WHEN_BROKEN
+        _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), C.byref(opts), d3, lo3, hi3,
                                                _ptr(active), _ptr(contain), _ptr(broken), _ptr(flags), _ptr(_scratch(dev)),
                                                _stream(dev)), "rt_contains_parity")
     return contain, broken, flags

@@ -142,10 +142,12 @@ class RayMeshIntersector:
 
     DEFAULT_CHECK_DIRECTION = (0.4395064455, 0.617598629942, 0.652231566745)   # reference :245-247
 
-    def contains_parity(self, points: torch.Tensor, direction, active: Optional[torch.Tensor] = None, out=None):
+    def contains_parity(self, points: torch.Tensor, direction, active: Optional[torch.Tensor] = None, out=None,
+                        stop_when_broken: bool = False):
         """Fused core of `contains_points`: (contain, broken, flags[2] = [any inside the AABB, any broken]) for one
         direction; with `active` / `out` a masked in-place update (see hops.contains_parity)."""
-        return hops.contains_parity(self.as_wrapper, points, direction, self._aabb_host[0], self._aabb_host[1], active, out)
+        return hops.contains_parity(self.as_wrapper, points, direction, self._aabb_host[0], self._aabb_host[1], active, out,
+                                    stop_when_broken)
 
     def contains_points(self, points: torch.Tensor, check_direction: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Bool[n] — is each point inside the (closed) mesh (reference :231-279).
@@ -184,11 +186,13 @@ def contains_points_flow(parity, points: torch.Tensor, check_direction, reduce_f
     # yields all False for the subset when none of the broken points lies inside the AABB (:243-244) or when
     # some point is broken again (a direction was given, :279); otherwise the subset's parity result.
     new_direction = draw_direction() if draw_direction is not None else (torch.rand(3) - 0.5).tolist()   # CPU generator, as :273
+    # The retry's per-point results only matter when NO point is broken again, so the launch may stop at the first one
+    # (typical: every ordinary outside point is 'broken' by the reference's definition, and stays so).
     was_broken = broken.clone()
-    _, _, flags = parity(points, new_direction, broken, (contain, broken))
+    _, _, flags = parity(points, new_direction, broken, (contain, broken), True)
     sub_inside, sub_broken = read(flags)
     if not sub_inside or sub_broken:
-        contain[was_broken] = False
+        contain.logical_and_(was_broken.logical_not_())      # contains[broken] = False, as two elementwise kernels
     return contain
 
 
