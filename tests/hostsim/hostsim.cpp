@@ -115,7 +115,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     std::vector<uint32_t> wide_src(lay.node_cap, 0);
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
-    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting();
+    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting(); t.flagged = 0;
     CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
@@ -231,7 +231,7 @@ extern "C" int hs_build_sah(const float* verts, int64_t nv, const int32_t* faces
     std::vector<uint32_t> wide_src(lay.node_cap, 0);
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
-    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting();
+    t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting(); t.flagged = 0;
     CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);

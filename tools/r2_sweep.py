@@ -19,7 +19,7 @@ dev = torch.device("cuda:0")
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 rows = []
-NAMES = {1: "direct", 2: "queued", 3: "coop_coherent", 4: "coop_incoherent", 5: "slots"}
+NAMES = {0: "auto", 1: "direct", 2: "queued", 3: "coop_coherent", 4: "coop_incoherent", 5: "slots"}
 
 
 def timed(fn, reps=5, warm=2):
@@ -64,6 +64,8 @@ for name in scenes:
     for qname, fn, b_out, smode in queries:
         for sched in [int(x) for x in os.environ.get("SWEEP_SCHEDS", "1,2,3,4,5").split(",")]:
             thrs = [0] if sched <= 2 else ([8, 16, 24, 32, 64] if sched == 3 else [16, 32, 64, 96])
+            if os.environ.get("SWEEP_THRS"):
+                thrs = [int(x) for x in os.environ["SWEEP_THRS"].split(",")] if sched > 2 else [0]
             if sched in (1, 3) and not coherent and name != "soup1m":
                 thrs = thrs[:1]          # late re-fill on incoherent batches: one point is enough
             if sched in (2, 4) and coherent and name == "small":

@@ -214,33 +214,65 @@ __device__ __forceinline__ void store_box_cg(BBox* p, const BBox& b, uint32_t le
     __stcg(reinterpret_cast<float4*>(p) + 1, make_float4(b.hx, b.hy, b.hz, __uint_as_float(right)));
 }
 
+// Bottom-up boxes.  One CTA owns a TILE of kRefitTile consecutive leaves (sorted order), one thread per leaf climbs:
+// the second thread to arrive at an inner node merges the two child boxes and goes on (Karras 2012).  In sorted Morton
+// order every Karras subtree is a contiguous leaf range [first, last] and an inner node's index is one end of its
+// range, so for all inner nodes whose range lies inside the tile - all but O(log) per tile - the arrival counter lives
+// in SHARED memory and the hand-over between the two children needs only a block-scope fence; only the nodes above a
+// tile boundary use the global counters and a device-scope fence.  (Round 1 used global atomics + __threadfence for
+// every node: 4.8 ms at 16.8 M triangles.)
+constexpr int kRefitTile = 1024;
 __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, int64_t nv,
                                                const int32_t* __restrict__ faces, int64_t n,
                                                const uint32_t* __restrict__ sorted_prim,
                                                const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                                               const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
                                                const uint32_t* __restrict__ parent, uint32_t* __restrict__ flags,
-                                               BBox* __restrict__ box) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        float v[9];
-        load_tri(verts, nv, faces, (int64_t)sorted_prim[k], v);
-        const BBox lb = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
-        store_box_cg(&box[(n - 1) + k], lb);
-        if (n == 1) continue;
-        uint32_t me = (uint32_t)((n - 1) + k);
-        uint32_t cur = parent[me];
-        BBox mine = lb;                                    // box of the subtree this thread has completed
-        for (;;) {
-            __threadfence();                               // publish box[me] before announcing it
-            if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arrival: sibling not ready
-            const uint32_t l = left[cur], rr = right[cur];
-            const uint32_t sibling = l == me ? rr : l;
-            mine = bbox_union(mine, load_box_cg(&box[sibling]));   // L1-bypassing load, ordered after the atomic
-            store_box_cg(&box[cur], mine, l, rr);
-            if (cur == 0u) break;
-            me = cur;
-            cur = parent[cur];
+                                               BBox* __restrict__ box, uint32_t leaf_max) {
+    __shared__ uint32_t s_flags[kRefitTile];
+    const int64_t tiles = (n + kRefitTile - 1) / kRefitTile;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t a = tile * kRefitTile;
+        const int64_t b = (a + kRefitTile < n ? a + kRefitTile : n) - 1;      // leaves [a, b]
+        for (int i = threadIdx.x; i < kRefitTile; i += blockDim.x) s_flags[i] = 0u;
+        __syncthreads();
+        for (int64_t k = a + threadIdx.x; k <= b; k += blockDim.x) {
+            float v[9];
+            load_tri(verts, nv, faces, (int64_t)sorted_prim[k], v);
+            const BBox lb = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+            store_box_cg(&box[(n - 1) + k], lb);
+            if (n == 1) continue;
+            uint32_t me = (uint32_t)((n - 1) + k);
+            uint32_t cur = parent[me];
+            BBox mine = lb;                                    // box of the subtree this thread has completed ...
+            uint32_t mine_count = 1u;                          // ... and its number of triangles
+            for (;;) {
+                const uint32_t f = first[cur], e = last[cur];
+                const bool local = (int64_t)f >= a && (int64_t)e <= b;
+                uint32_t arrived;
+                if (local) {
+                    __threadfence_block();                     // publish box[me] to the CTA before announcing it
+                    arrived = atomicAdd(&s_flags[cur - (uint32_t)a], 1u);
+                } else {
+                    __threadfence();                           // ... to the device
+                    arrived = atomicAdd(&flags[cur], 1u);
+                }
+                if (arrived == 0u) break;                      // first arrival: sibling not ready
+                const uint32_t l = left[cur], rr = right[cur];
+                const uint32_t sibling = l == me ? rr : l;
+                mine = bbox_union(mine, load_box_cg(&box[sibling]));   // L1-bypassing load, ordered after the atomic
+                // child references ride in the pad words; bit 31 = "covers more than leaf_max triangles" (the collapse
+                // then needs no first/last loads to decide whether a child can be expanded)
+                const uint32_t total = e - f + 1u, sib_count = total - mine_count;
+                const uint32_t me_bit = mine_count > leaf_max ? 0x80000000u : 0u, sib_bit = sib_count > leaf_max ? 0x80000000u : 0u;
+                store_box_cg(&box[cur], mine, l | (l == me ? me_bit : sib_bit), rr | (l == me ? sib_bit : me_bit));
+                mine_count = total;
+                if (cur == 0u) break;
+                me = cur;
+                cur = parent[cur];
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -380,11 +412,13 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         k_morton<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state, w.keys, w.vals);
         RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream));
         if (n > 1) k_karras<<<g, 256, 0, stream>>>(w.keys, n, w.left, w.right, w.first, w.last, w.parent);
-        k_refit<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.vals, w.left, w.right, w.parent, w.flags, w.box);
+        k_refit<<<grid_for((n + kRefitTile - 1) / kRefitTile * 256, 256, dev.sm_count, 8), 256, 0, stream>>>(
+            vertices, n_verts, faces, n, w.vals, w.left, w.right, w.first, w.last, w.parent, w.flags, w.box,
+            (uint32_t)leaf_tris_setting());
 
         BinaryTree t;
         t.n = n; t.left = w.left; t.right = w.right; t.first = w.first; t.last = w.last; t.box = w.box;
-        t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting();
+        t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting(); t.flagged = 1;
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
         o.parent = w.wide_parent;

@@ -134,7 +134,10 @@ struct BinaryTree {
     const BBox* box;              // [2n-1] internal boxes then leaf boxes
     const uint32_t* sorted_prim;  // [n] triangle id at each sorted position
     int leaf_max;                 // subtrees of <= leaf_max triangles become one leaf slot (1..kLeafMaxTris)
+    int flagged;                  // child references in the box pads carry "covers more than leaf_max triangles" in bit 31
+                                  // (written by the GPU refit pass), so expanding a child needs no first/last loads
 };
+constexpr uint32_t kRefMask = 0x7fffffffu;
 
 RT_HD uint32_t bt_count(const BinaryTree& t, uint32_t ref) {
     return ref >= (uint32_t)(t.n - 1) ? 1u : t.last[ref] - t.first[ref] + 1u;
@@ -190,6 +193,43 @@ struct CollapseOut {
     uint32_t* tri_count;
     uint32_t node_cap;
 };
+
+// Allocates the node's inner children and triangle records from the two global bump counters.  On the device the
+// threads of a warp that arrive together make ONE atomic per counter (the leader adds the group's total, every
+// thread takes its exclusive prefix): with one atomic per node the two counters - single addresses hit by every
+// thread of the grid - serialise in the L2 atomic unit (2.6 M nodes x 2 atomics was most of the collapse time at
+// 16.8 M triangles).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void alloc_children(const CollapseOut& o, uint32_t n_inner, uint32_t n_tris, uint32_t& child_base,
+                                               uint32_t& tri_base) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    // exclusive prefix and total over the lanes that arrived together (the group may have holes: walk its members);
+    // both counts ride in one 64-bit value (no carry: a warp allocates far fewer than 2^32 of either)
+    const unsigned long long mine = ((unsigned long long)n_tris << 32) | n_inner;
+    unsigned long long total = 0, excl = 0;
+    for (unsigned rest = m; rest != 0u; rest &= rest - 1u) {
+        const int src = __ffs((int)rest) - 1;
+        const unsigned long long v = __shfl_sync(m, mine, src);
+        if (src < lane) excl += v;
+        total += v;
+    }
+    unsigned long long base = 0;
+    if (lane == leader) {
+        const uint32_t nb = (uint32_t)total ? atomicAdd(o.node_count, (uint32_t)total) : 0u;
+        const uint32_t tb = (uint32_t)(total >> 32) ? atomicAdd(o.tri_count, (uint32_t)(total >> 32)) : 0u;
+        base = ((unsigned long long)tb << 32) | nb;
+    }
+    base = __shfl_sync(m, base, leader);
+    child_base = n_inner ? (uint32_t)base + (uint32_t)excl : 0u;
+    tri_base = n_tris ? (uint32_t)(base >> 32) + (uint32_t)(excl >> 32) : 0u;
+}
+#else
+inline void alloc_children(const CollapseOut& o, uint32_t n_inner, uint32_t n_tris, uint32_t& child_base, uint32_t& tri_base) {
+    child_base = n_inner ? atomic_add_u32(o.node_count, n_inner) : 0u;
+    tri_base = n_tris ? atomic_add_u32(o.tri_count, n_tris) : 0u;
+}
+#endif
 
 // Builds wide node `w` from the binary subtree `wide_src[w]`.  Greedy surface-area expansion:
 // starting from the two children, repeatedly replace the child with the largest box that is
@@ -334,16 +374,20 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     } else {
         // the box record of an inner binary node carries its two child references in the pad words
         // (written by the refit pass), so expanding a child costs no extra dependent load
-        ref[0] = box_left(nb); ref[1] = box_right(nb); k = 2;
-        for (int i = 0; i < 2; ++i) { cb[i] = t.box[ref[i]]; inner[i] = bt_expandable(t, ref[i]); area[i] = box_area(cb[i]); }
+        const uint32_t raw0 = box_left(nb), raw1 = box_right(nb);
+        ref[0] = raw0 & kRefMask; ref[1] = raw1 & kRefMask; k = 2;
+        inner[0] = t.flagged ? (raw0 >> 31) != 0u : bt_expandable(t, ref[0]);
+        inner[1] = t.flagged ? (raw1 >> 31) != 0u : bt_expandable(t, ref[1]);
+        for (int i = 0; i < 2; ++i) { cb[i] = t.box[ref[i]]; area[i] = box_area(cb[i]); }
         while (k < 8) {
             int best = -1; float ba = -1.0f;
             for (int i = 0; i < k; ++i)
                 if (inner[i] && area[i] > ba) { best = i; ba = area[i]; }
             if (best < 0) break;
-            const uint32_t l = box_left(cb[best]), r = box_right(cb[best]);
-            ref[best] = l; cb[best] = t.box[l]; inner[best] = bt_expandable(t, l); area[best] = box_area(cb[best]);
-            ref[k] = r; cb[k] = t.box[r]; inner[k] = bt_expandable(t, r); area[k] = box_area(cb[k]);
+            const uint32_t lraw = box_left(cb[best]), rraw = box_right(cb[best]);
+            const uint32_t l = lraw & kRefMask, r = rraw & kRefMask;
+            ref[best] = l; cb[best] = t.box[l]; inner[best] = t.flagged ? (lraw >> 31) != 0u : bt_expandable(t, l); area[best] = box_area(cb[best]);
+            ref[k] = r; cb[k] = t.box[r]; inner[k] = t.flagged ? (rraw >> 31) != 0u : bt_expandable(t, r); area[k] = box_area(cb[k]);
             ++k;
         }
         // free slots left: split multi-triangle leaves (largest box first) so that each triangle
@@ -353,7 +397,7 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             for (int i = 0; i < k; ++i)
                 if (!inner[i] && ref[i] < (uint32_t)(t.n - 1) && area[i] > ba) { best = i; ba = area[i]; }
             if (best < 0) break;
-            const uint32_t l = box_left(cb[best]), r = box_right(cb[best]);
+            const uint32_t l = box_left(cb[best]) & kRefMask, r = box_right(cb[best]) & kRefMask;
             ref[best] = l; cb[best] = t.box[l]; inner[best] = false; area[best] = box_area(cb[best]);
             ref[k] = r; cb[k] = t.box[r]; inner[k] = false; area[k] = box_area(cb[k]);
             ++k;
@@ -379,8 +423,8 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
         }
         child_in_slot[bs] = i;
     }
-    const uint32_t child_base = n_inner ? atomic_add_u32(o.node_count, n_inner) : 0u;
-    const uint32_t tri_base = n_tris ? atomic_add_u32(o.tri_count, n_tris) : 0u;
+    uint32_t child_base, tri_base;
+    alloc_children(o, n_inner, n_tris, child_base, tri_base);
 
     BBox slot_box[8];
     uint32_t present = 0;

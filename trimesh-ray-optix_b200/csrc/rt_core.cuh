@@ -186,7 +186,8 @@ RT_HD bool tri_test(const Ray& r, float v0x, float v0y, float v0z, float v1x, fl
         if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     }
     const float det = fadd(fadd(U, V), W);
-    if (!(det != 0.0f)) return false;   // also rejects NaN
+    if (!(det != 0.0f)) return false;   // det == 0: degenerate / edge-on.  A NaN det passes here (NaN != 0) and leaves t = NaN,
+                                        // which every visitor drops with its `t > 0` test
     const float Az = fmul(r.Sz, Akz), Bz = fmul(r.Sz, Bkz), Cz = fmul(r.Sz, Ckz);
     const float T = ffma(U, Az, ffma(V, Bz, fmul(W, Cz)));
     h.t = fdiv(T, det);
@@ -257,6 +258,18 @@ RT_HD uint32_t shift_in_sign(float x, uint32_t acc) {
 }
 #endif
 
+// (acc << 1) | (signbit(a) | signbit(b) | signbit(c))
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t shift_in_signs(float a, float b, float c, uint32_t acc) {
+    return __funnelshift_l(__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c), acc, 1);
+}
+#else
+RT_HD uint32_t shift_in_signs(float a, float b, float c, uint32_t acc) {
+    union { float f; uint32_t u; } x, y, z; x.f = a; y.f = b; z.f = c;
+    return (acc << 1) | ((x.u | y.u | z.u) >> 31);
+}
+#endif
+
 RT_HD uint32_t spread3(uint32_t x) {   // bit i (0..7) -> bit 3i
     x = (x | (x << 8)) & 0x0000f00fu;
     x = (x | (x << 4)) & 0x000c30c3u;
@@ -294,8 +307,10 @@ RT_HD uint32_t finish_masks(uint32_t hm8, uint32_t imask, uint32_t trimask, uint
 #endif
 }
 
+// The ray interval is (0, tmax): `tmin` is kept in the signature for the call sites' readability and must be 0.
 RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
                          float tmin, float tmax) {
+    (void)tmin;
     const float px = as_float(n0.x), py = as_float(n0.y), pz = as_float(n0.z);
     const float sx = as_float((n0.w & 0xffu) << 23);
     const float sy = as_float(((n0.w >> 8) & 0xffu) << 23);
@@ -319,6 +334,10 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
     // pipe, leaving one ALU-pipe instruction per child (the ALU pipe is the kernel's bottleneck)
     uint32_t miss = 0;
     const uint32_t magic = r.magic;
+#if defined(__CUDA_ARCH__) && defined(RT_NODE_FFMA2)
+    const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
+    const float2 cx2 = make_float2(cnx, cfx), cy2 = make_float2(cny, cfy), cz2 = make_float2(cnz, cfz);
+#endif
 #pragma unroll
     for (int half = 1; half >= 0; --half) {
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
@@ -326,16 +345,33 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
         const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
         const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
         const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
-#define RT_SLAB(I)                                                                                              \
-        {                                                                                                       \
+#if defined(__CUDA_ARCH__) && defined(RT_NODE_FFMA2)
+        // packed FP32 FMA of sm_100 (fma.rn.f32x2): the near and the far plane of one axis in one instruction - same
+        // IEEE results lane by lane, half the issue slots
+#define RT_PLANES(I)                                                                                            \
+            const float2 px2 = __ffma2_rn(make_float2(byte_plus_32768<I>(nx, magic), byte_plus_32768<I>(fx, magic)), ax2, cx2); \
+            const float2 py2 = __ffma2_rn(make_float2(byte_plus_32768<I>(ny, magic), byte_plus_32768<I>(fy, magic)), ay2, cy2); \
+            const float2 pz2 = __ffma2_rn(make_float2(byte_plus_32768<I>(nz, magic), byte_plus_32768<I>(fz, magic)), az2, cz2); \
+            const float tnx = px2.x, tfx = px2.y, tny = py2.x, tfy = py2.y, tnz = pz2.x, tfz = pz2.y;
+#else
+#define RT_PLANES(I)                                                                                            \
             const float tnx = fmaf(byte_plus_32768<I>(nx, magic), ax, cnx), tfx = fmaf(byte_plus_32768<I>(fx, magic), ax, cfx); \
             const float tny = fmaf(byte_plus_32768<I>(ny, magic), ay, cny), tfy = fmaf(byte_plus_32768<I>(fy, magic), ay, cfy); \
-            const float tnz = fmaf(byte_plus_32768<I>(nz, magic), az, cnz), tfz = fmaf(byte_plus_32768<I>(fz, magic), az, cfz); \
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                          \
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                          \
-            miss = shift_in_sign(tf - tn, miss);                                                                \
+            const float tnz = fmaf(byte_plus_32768<I>(nz, magic), az, cnz), tfz = fmaf(byte_plus_32768<I>(fz, magic), az, cfz);
+#endif
+        // A slot is missed iff min(tf, tmax) < max(tn, tmin) with tmin = 0.  The clamps are not applied to the values:
+        // the three conditions tf3 < tn3, tmax < tn3 and tf3 < 0 are read off sign bits (two FADDs on the FMA pipe and
+        // one LOP3 instead of two FMNMX on the ALU pipe, which is the kernel's bottleneck); NaNs stay conservative
+        // (FMNMX3 drops them, a NaN difference carries no sign).
+#define RT_SLAB(I)                                                                                              \
+        {                                                                                                       \
+            RT_PLANES(I)                                                                                        \
+            const float tn3 = fmaxf(fmaxf(tnx, tny), tnz);                                                      \
+            const float tf3 = fminf(fminf(tfx, tfy), tfz);                                                      \
+            miss = shift_in_signs(tf3 - tn3, tmax - tn3, tf3, miss);                                            \
         }
         RT_SLAB(3) RT_SLAB(2) RT_SLAB(1) RT_SLAB(0)
+#undef RT_PLANES
 #undef RT_SLAB
     }
     const uint32_t hm8 = ~miss & 0xffu;

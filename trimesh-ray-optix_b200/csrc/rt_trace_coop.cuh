@@ -29,6 +29,7 @@ namespace rt {
 #define RT_PAIR_CAP 128
 #endif
 constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
+constexpr int kTailLanes = 4;          // <= this many lanes with node work: test listed pairs every step
 constexpr int kRayWords = 7;           // resident part of a ray in shared memory: S(3), permuted origin(3), kzf
 
 // POOL = incoherent batches: rays are prepared 32 at a time into a shared-memory pool and lanes re-fill early;
@@ -140,7 +141,9 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         const int busy = 32 - __popc(done_mask);
         const bool want_refill = done_mask != 0u && busy < ((exhausted && pool_count == 0) ? 1 : p.refill_threshold);
         if (n_pend > 0) {
-            bool go = n_pend >= p.tri_threshold;
+            // few lanes left with node work (the tail of a launch, or a lone long ray): test at once, so that tmax shrinks
+            // before the next node step instead of after tri_threshold pairs have trickled in
+            bool go = n_pend >= p.tri_threshold || busy <= kTailLanes;
             if (!go && n_pend == kPairCap) go = true;                                                      // list full (triangles may be waiting in ty)
             if (!go && want_refill) go = __any_sync(0xffffffffu, active && nodes_done && my_pend != 0);   // rays wait to retire
             if (go) flush();
