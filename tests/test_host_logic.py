@@ -87,3 +87,62 @@ def test_symmetric_buffer_layouts_are_aligned_and_disjoint():
         order = sorted(need, key=lambda k: lay[k])
         for a, b in zip(order, order[1:] + ["bytes"]):
             assert lay[a] % 256 == 0 and lay[a] + need[a] <= lay[b]
+
+
+def test_blob_header_validation_refuses_truncated_and_corrupt_blobs():
+    """ops.validate_header (used by build, adopt and load): what a kernel relies on is checked on the host first."""
+    import struct
+
+    import torch
+
+    from triro.backend import ops
+
+    def header(n_tris=10, n_nodes=3, depth=2, nodes_off=None, parents_off=None, used=None, overflow=0, magic=ops.BLOB_MAGIC, abi=ops.ABI_VERSION):
+        nodes_off = 256 + 48 * n_tris + 16 if nodes_off is None else nodes_off
+        parents_off = (nodes_off + 80 * n_nodes + 255) // 256 * 256 if parents_off is None else parents_off
+        used = parents_off + 4 * n_nodes if used is None else used
+        raw = bytearray(256)
+        struct.pack_into("<6I", raw, 0, magic, abi, n_tris, n_nodes, depth, n_nodes + 2)
+        struct.pack_into("<3Q", raw, 24, 256, nodes_off, used)
+        struct.pack_into("<2I", raw, 72, 0, overflow)
+        struct.pack_into("<Q", raw, 80, parents_off)
+        return bytes(raw), used
+
+    raw, used = header()
+    ops.validate_header(ops.parse_header(raw), used)                           # consistent: accepted
+    with pytest.raises(ValueError):
+        ops.validate_header(ops.parse_header(raw), used - 1)                   # tensor shorter than used_bytes
+    with pytest.raises(RuntimeError):
+        ops.validate_header(ops.parse_header(header(depth=ops.MAX_DEPTH + 1)[0]), 1 << 20)   # deeper than the traversal stack
+    with pytest.raises(RuntimeError):
+        ops.validate_header(ops.parse_header(header(overflow=1)[0]), 1 << 20)
+    with pytest.raises(ValueError):
+        ops.validate_header(ops.parse_header(header(nodes_off=256 + 48 * 5)[0]), 1 << 20)    # nodes overlap the triangle records
+    with pytest.raises(ValueError):
+        ops.validate_header(ops.parse_header(header(parents_off=256 + 48 * 10 + 16 + 80)[0]), 1 << 20)   # parents overlap the nodes
+    # adopt() on a host tensor applies the same checks (a blob straight from torch.load / a gloo broadcast)
+    blob = torch.zeros(used, dtype=torch.uint8)
+    blob[:256] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    assert ops.AccelStructure().adopt(blob).header["n_nodes"] == 3
+    with pytest.raises(ValueError):
+        ops.AccelStructure().adopt(blob[: used // 2].clone())
+    bad = blob.clone(); bad[0] = 0
+    with pytest.raises(ValueError):
+        ops.AccelStructure().adopt(bad)
+
+
+def test_trace_opts_defaults_and_knobs_are_per_call():
+    from triro.backend import ops
+
+    o = ops.trace_opts()
+    assert (o.tmax, o.ray_first, o.ray_count, o.schedule) == (1.0e7, 0, 0, ops._KNOBS["schedule"])
+    old = ops.set_knobs(schedule=ops.SCHED_SLOTS, tri_threshold=48)
+    try:
+        o = ops.trace_opts(None, 7, 9)
+        assert (o.schedule, o.tri_threshold, o.ray_first, o.ray_count) == (ops.SCHED_SLOTS, 48, 7, 9)
+    finally:
+        ops.set_knobs(**old)
+    assert ops.trace_opts().schedule == old["schedule"]
+    with pytest.raises(KeyError):
+        ops.set_knobs(nonsense=1)
+    assert ops.allhits_window_rays(8, 1 << 20) == (1 << 20) // 128 and ops.allhits_window_rays(64, 1) == 1024

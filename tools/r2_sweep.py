@@ -70,7 +70,7 @@ for name in scenes:
                 thrs = thrs[:1]          # late re-fill on incoherent batches: one point is enough
             if sched in (2, 4) and coherent and name == "small":
                 thrs = thrs[:1]
-            refills = [int(x) for x in os.environ.get("SWEEP_REFILL", "0").split(",")] if sched >= 4 else [0]
+            refills = [int(x) for x in os.environ.get("SWEEP_REFILL", "0").split(",")] if sched >= 3 else [0]
             for thr, refill in [(t, rf) for t in thrs for rf in refills]:
                 old = hops.set_knobs(schedule=sched, tri_threshold=thr, refill_threshold=refill)
                 try:

@@ -347,7 +347,8 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
         const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
 #if defined(__CUDA_ARCH__) && defined(RT_NODE_FFMA2)
         // packed FP32 FMA of sm_100 (fma.rn.f32x2): the near and the far plane of one axis in one instruction - same
-        // IEEE results lane by lane, half the issue slots
+        // IEEE results lane by lane, half the issue slots.  Measured: +0.8 % on camera rays, -1...-4 % on incoherent
+        // batches (profiles/r2_sweeps.md) - off by default.
 #define RT_PLANES(I)                                                                                            \
             const float2 px2 = __ffma2_rn(make_float2(byte_plus_32768<I>(nx, magic), byte_plus_32768<I>(fx, magic)), ax2, cx2); \
             const float2 py2 = __ffma2_rn(make_float2(byte_plus_32768<I>(ny, magic), byte_plus_32768<I>(fy, magic)), ay2, cy2); \
@@ -359,10 +360,11 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
             const float tny = fmaf(byte_plus_32768<I>(ny, magic), ay, cny), tfy = fmaf(byte_plus_32768<I>(fy, magic), ay, cfy); \
             const float tnz = fmaf(byte_plus_32768<I>(nz, magic), az, cnz), tfz = fmaf(byte_plus_32768<I>(fz, magic), az, cfz);
 #endif
-        // A slot is missed iff min(tf, tmax) < max(tn, tmin) with tmin = 0.  The clamps are not applied to the values:
-        // the three conditions tf3 < tn3, tmax < tn3 and tf3 < 0 are read off sign bits (two FADDs on the FMA pipe and
-        // one LOP3 instead of two FMNMX on the ALU pipe, which is the kernel's bottleneck); NaNs stay conservative
-        // (FMNMX3 drops them, a NaN difference carries no sign).
+        // A slot is missed iff min(tf, tmax) < max(tn, 0).  Default: clamp, subtract, collect the sign with a funnel shift
+        // (FADD runs on the FMA pipe, leaving one ALU-pipe instruction per slot besides the FMNMX).  RT_NODE_SIGNBITS reads
+        // the three conditions tf3 < tn3, tmax < tn3, tf3 < 0 off sign bits instead (2 FADD + 1 LOP3 for 2 FMNMX: fewer
+        // ALU-pipe instructions) - measured 1-3 % SLOWER on every workload (profiles/r2_sweeps.md), so it is off.
+#if defined(RT_NODE_SIGNBITS)
 #define RT_SLAB(I)                                                                                              \
         {                                                                                                       \
             RT_PLANES(I)                                                                                        \
@@ -370,6 +372,15 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
             const float tf3 = fminf(fminf(tfx, tfy), tfz);                                                      \
             miss = shift_in_signs(tf3 - tn3, tmax - tn3, tf3, miss);                                            \
         }
+#else
+#define RT_SLAB(I)                                                                                              \
+        {                                                                                                       \
+            RT_PLANES(I)                                                                                        \
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                          \
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                          \
+            miss = shift_in_sign(tf - tn, miss);                                                                \
+        }
+#endif
         RT_SLAB(3) RT_SLAB(2) RT_SLAB(1) RT_SLAB(0)
 #undef RT_PLANES
 #undef RT_SLAB
