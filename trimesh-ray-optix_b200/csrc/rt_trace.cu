@@ -7,9 +7,17 @@
 // (shaders.cu:27-63).
 //
 // Execution model: persistent CTAs (grid = SMs x resident CTAs), one ray per lane.  A warp
-// advances all its rays one wide node at a time (rt::trav_step) and, whenever fewer than
-// kRefillThreshold lanes are still busy, retires the finished rays and re-fills those lanes
-// from a global ray counter with one warp-aggregated atomic (Aila & Laine 2009).
+// advances all its rays one wide node at a time and, whenever too few lanes are still busy,
+// retires the finished rays and re-fills those lanes from a global ray counter with one
+// warp-aggregated atomic (Aila & Laine 2009).  Five schedules give bit-identical results
+// (rt_trace_opts::schedule):
+//   this file           k_trace<MODE, STATS, QUEUED>: every lane tests its own triangles, inside the node
+//                       step (direct) or from a per-lane queue (queued; the all-hits path)
+//   rt_trace_coop.cuh   k_trace_coop: (triangle, lane) pairs in a warp-shared list, tested by all 32 lanes -
+//                       the default for every query but all-hits
+//   rt_trace_slots.cuh  k_trace_slots: rays live in per-warp slots handed around by queues (opt-in)
+// launch() below resolves rt_trace_opts (tmax, ray window, schedule, knobs) - there is no state
+// behind a call: no environment variable, no thread-local setting, one kernel launch.
 #include <stdlib.h>
 #include <type_traits>
 #define RT_MASK_LUT 1
@@ -543,12 +551,9 @@ static int occupancy(int sched, int* per_sm) {
                 return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_slots<MODE, STATS>, kTraceThreads, 0);
             return (int)cudaErrorInvalidValue;
         default:
-            if constexpr (MODE != kAllHits) {
-                if (sched == RT_SCHED_COOP_COHERENT)
-                    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, false>, kTraceThreads, 0);
-                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, true>, kTraceThreads, 0);
-            }
-            return (int)cudaErrorInvalidValue;
+            if (sched == RT_SCHED_COOP_COHERENT)
+                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, false>, kTraceThreads, 0);
+            return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, true>, kTraceThreads, 0);
     }
 }
 
@@ -588,13 +593,16 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     // Scheduling: rays that share one origin (a stride-0 broadcast, i.e. camera / primary rays, reference
     // README.md:38 and test/performance_test.py:36-41) are coherent and mostly short: lanes re-fill late.
     // Anything else is treated as incoherent: rays prepared 32 at a time into a pool, early re-fill.  Both use
-    // the warp-cooperative triangle tests of rt_trace_coop.cuh; all-hits keeps the per-lane queues.
+    // the warp-cooperative triangle tests of rt_trace_coop.cuh.
     const bool coherent = MODE != kContains && (p.o_mode == kConstant || pinhole);
     int sched = o.schedule;
     RT_REQUIRE(sched >= RT_SCHED_AUTO && sched <= RT_SCHED_SLOTS, RT_ERR_INVALID, "%s: unknown schedule %d", fn, sched);
     if (sched == RT_SCHED_AUTO) sched = coherent ? RT_SCHED_COOP_COHERENT : RT_SCHED_COOP_INCOHERENT;
+    // all hits on incoherent batches: the per-lane queues stay the default (1 M-triangle soup 13.9 vs 14.3 ms cooperative:
+    // recording a hit - attributes + a 16-byte staging store - is heavy work for the few lanes of a pair batch that hit;
+    // the 4.19 M heightfield would gain 7 %, camera rays gain 5 % and do take the cooperative kernel)
+    if (MODE == kAllHits && o.schedule == RT_SCHED_AUTO && !coherent) sched = RT_SCHED_QUEUED;
     if (sched == RT_SCHED_SLOTS && !kHasSlots<MODE>) sched = RT_SCHED_COOP_INCOHERENT;      // contains / all hits
-    if (MODE == kAllHits && sched >= RT_SCHED_COOP_COHERENT) sched = sched == RT_SCHED_COOP_COHERENT ? RT_SCHED_DIRECT : RT_SCHED_QUEUED;
     const bool early = sched == RT_SCHED_QUEUED || sched == RT_SCHED_COOP_INCOHERENT || sched == RT_SCHED_SLOTS;
     const bool coop = sched >= RT_SCHED_COOP_COHERENT;
     auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
@@ -622,10 +630,8 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
             if constexpr (kHasSlots<MODE>) k_trace_slots<MODE, STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
             break;
         default:
-            if constexpr (MODE != kAllHits) {
-                if (sched == RT_SCHED_COOP_COHERENT) k_trace_coop<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
-                else k_trace_coop<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
-            }
+            if (sched == RT_SCHED_COOP_COHERENT) k_trace_coop<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            else k_trace_coop<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
     }
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;

@@ -1,7 +1,7 @@
 // rt_trace_coop.cuh — traversal kernel with WARP-COOPERATIVE triangle tests (included by rt_trace.cu).
 //
-// Same role as k_trace (rt_trace.cu): replaces optixTrace + the closest/first/any/count programs of the
-// reference (triro/backend/shaders.cu:67-194) and the two count launches of contains_points
+// Same role as k_trace (rt_trace.cu): replaces optixTrace + the closest/first/any/count/all-hits programs of the
+// reference (triro/backend/shaders.cu:67-246) and the two count launches of contains_points
 // (triro/ray/ray_optix.py:254-260).  What differs from k_trace is WHO tests a triangle:
 //
 //   * every lane still owns one ray and walks the BVH8 one wide node per step, but a hit leaf slot is
@@ -37,12 +37,12 @@ constexpr int kRayWords = 7;           // resident part of a ray in shared memor
 template <int MODE, bool STATS, bool POOL>
 __global__ void __launch_bounds__(kTraceThreads, (MODE == kClosest && POOL) ? RT_TRACE_MIN_BLOCKS : RT_TRACE_MIN_BLOCKS_LIGHT)
 k_trace_coop(const __grid_constant__ TraceParams p) {
-    static_assert(MODE != kAllHits, "all-hits keeps the per-lane schedule (deterministic record order)");
     constexpr bool kKey = MODE == kClosest || MODE == kFirst;
     __shared__ float s_ray[kRayWords][kTraceThreads];
     __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim
     __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
     __shared__ float s_attr[MODE == kClosest ? 6 : 1][kTraceThreads];    // loc(3), uv(2), front
+    __shared__ unsigned long long s_rayidx[MODE == kAllHits ? kTraceThreads : 1];   // all hits: where the owner's records go
     __shared__ uint2 s_pair[kTraceThreads / 32][kPairCap];               // (triangle record, owner lane)
     __shared__ float s_pool[POOL ? kPoolWords : 1][kTraceThreads];
     init_mask_luts();
@@ -102,6 +102,17 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                         if (key < s_best[col]) { atomicMin(&s_best[col], key); won = true; }
                     } else if constexpr (MODE == kAny) {
                         if (h.t < p.tmax) s_cnt[col] = 1u;
+                    } else if constexpr (MODE == kAllHits) {
+                        // reference __anyhit__intersectsLocation (shaders.cu:207-224): the first max_hits hits found are
+                        // recorded (which ones, beyond max_hits, is traversal order there and test order here), all counted
+                        if (h.t < p.tmax) {
+                            const uint32_t k = atomicAdd(&s_cnt[col], 1u);
+                            if (k < (uint32_t)p.max_hits) {
+                                const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+                                p.staging[(size_t)s_rayidx[col] * p.max_hits + k] =
+                                    make_uint4(a.w, __float_as_uint(at.lx), __float_as_uint(at.ly), __float_as_uint(at.lz));
+                            }
+                        }
                     } else {
                         if (h.t < p.tmax) atomicAdd(&s_cnt[col], 1u);
                     }
@@ -129,6 +140,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         s_ray[3][mycol] = t.okx; s_ray[4][mycol] = t.oky; s_ray[5][mycol] = t.okz;
         s_ray[6][mycol] = __int_as_float(t.kzf);
         if constexpr (kKey) s_best[mycol] = key_init; else s_cnt[mycol] = 0u;
+        if constexpr (MODE == kAllHits) s_rayidx[mycol] = (unsigned long long)r;
         tmax = p.tmax;
         trav_init(tv);
         nodes_done = false;
@@ -184,6 +196,10 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     const uint32_t c = s_cnt[mycol];
                     if (STATS) { ++st_rays; st_hits += c > 0u; }
                     if (p.count) p.count[r] = (int32_t)c;
+                    active = false;
+                } else if constexpr (MODE == kAllHits) {
+                    const uint32_t c = s_cnt[mycol];
+                    p.count[r] = (int32_t)(c < (uint32_t)p.max_hits ? c : (uint32_t)p.max_hits);     // ray.cpp:334-335
                     active = false;
                 } else if constexpr (MODE == kContains) {
                     // reference: ray_optix.py:238-267 — count along +dir, then along -dir
