@@ -116,7 +116,8 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
     t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting(); t.flagged = 0;
-    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
+    std::vector<uint32_t> tri_pos((size_t)n, 0);
+    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data(); o.tri_pos = tri_pos.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
     uint32_t begin = 0, end = 1, depth = 0;
@@ -126,7 +127,7 @@ extern "C" int hs_build(const float* verts, int64_t nv, const int32_t* faces, in
         begin = end;
         end = node_count < lay.node_cap ? node_count : lay.node_cap;
     }
-    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, vals.data(), verts, nv, faces);
+    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, tri_pos.data(), vals.data(), verts, nv, faces);
     h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
     for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
     h.node_overflow = node_count > lay.node_cap ? 1u : 0u;
@@ -232,7 +233,8 @@ extern "C" int hs_build_sah(const float* verts, int64_t nv, const int32_t* faces
     uint32_t node_count = 1, tri_count = 0;
     BinaryTree t; t.n = n; t.left = left.data(); t.right = right.data(); t.first = first.data(); t.last = last.data();
     t.box = box.data(); t.sorted_prim = vals.data(); t.leaf_max = leaf_setting(); t.flagged = 0;
-    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data();
+    std::vector<uint32_t> tri_pos((size_t)n, 0);
+    CollapseOut o; o.nodes = blob + lay.nodes_offset; o.tris = blob + lay.tris_offset; o.wide_src = wide_src.data(); o.tri_pos = tri_pos.data();
     o.node_count = &node_count; o.tri_count = &tri_count; o.node_cap = lay.node_cap;
     o.parent = reinterpret_cast<uint32_t*>(blob + lay.parents_offset);
     uint32_t begin = 0, end = 1, depth = 0;
@@ -242,7 +244,7 @@ extern "C" int hs_build_sah(const float* verts, int64_t nv, const int32_t* faces
         begin = end;
         end = node_count < lay.node_cap ? node_count : lay.node_cap;
     }
-    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, vals.data(), verts, nv, faces);
+    for (int64_t i = 0; i < n; ++i) fill_tri_record(blob + lay.tris_offset, (uint32_t)i, tri_pos.data(), vals.data(), verts, nv, faces);
     h.n_nodes = node_count; h.depth = depth; h.used_bytes = lay.nodes_offset + (uint64_t)node_count * 80u;
     for (int a = 0; a < 3; ++a) { h.aabb_lo[a] = lo[a]; h.aabb_hi[a] = hi[a]; }
     h.node_overflow = node_count > lay.node_cap ? 1u : 0u;

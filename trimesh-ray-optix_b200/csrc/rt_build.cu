@@ -178,12 +178,13 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ verts,
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = ord2f(st->bounds_lo[a]); hi[a] = ord2f(st->bounds_hi[a]); }
     morton_scale(lo, hi, inv);
+    const int drop = 3 * (21 - morton_axis_bits(n));      // low bits that do not take part in the ordering
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float v[9];
         load_tri(verts, nv, faces, i, v);
         const BBox b = tri_bbox(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
-        keys[i] = morton63(0.5f * (b.lx + b.hx), 0.5f * (b.ly + b.hy), 0.5f * (b.lz + b.hz), lo, inv);
+        keys[i] = morton63(0.5f * (b.lx + b.hx), 0.5f * (b.ly + b.hy), 0.5f * (b.lz + b.hz), lo, inv) >> drop;
         vals[i] = (uint32_t)i;
     }
 }
@@ -298,10 +299,11 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, CollapseOut o, c
 
 __global__ void __launch_bounds__(256) k_fill_tris(const float* __restrict__ verts, int64_t nv,
                                                    const int32_t* __restrict__ faces, int64_t n,
+                                                   const uint32_t* __restrict__ tri_pos,
                                                    const uint32_t* __restrict__ sorted_prim, uint8_t* tris) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        fill_tri_record(tris, (uint32_t)i, sorted_prim, verts, nv, faces);
+        fill_tri_record(tris, (uint32_t)i, tri_pos, sorted_prim, verts, nv, faces);
 }
 
 // The (parent << 3 | slot) array of the wide nodes (only rt_bvh_refit reads it) is built in the workspace and placed
@@ -410,7 +412,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         const int g = grid_for(n, 256, dev.sm_count, 8);
         k_scene_bounds<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state);
         k_morton<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state, w.keys, w.vals);
-        RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream));
+        RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream, morton_sort_passes(n)));
         if (n > 1) k_karras<<<g, 256, 0, stream>>>(w.keys, n, w.left, w.right, w.first, w.last, w.parent);
         k_refit<<<grid_for((n + kRefitTile - 1) / kRefitTile * 256, 256, dev.sm_count, 8), 256, 0, stream>>>(
             vertices, n_verts, faces, n, w.vals, w.left, w.right, w.first, w.last, w.parent, w.flags, w.box,
@@ -421,6 +423,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting(); t.flagged = 1;
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
+        o.tri_pos = reinterpret_cast<uint32_t*>(w.keys);      // the sorted keys are dead once the hierarchy exists (8n bytes, n words needed)
         o.parent = w.wide_parent;
         o.node_count = &w.state->node_count; o.tri_count = &w.state->tri_count; o.node_cap = lay.node_cap;
         int per_sm = 0;
@@ -432,7 +435,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         BuildState* stp = w.state;
         void* args[] = {&t, &o, (void*)&vertices, (void*)&n_verts, (void*)&faces, &stp};
         RT_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(cgrid), dim3(128), args, 0, stream));
-        k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.vals, blob8 + lay.tris_offset);
+        k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, o.tri_pos, w.vals, blob8 + lay.tris_offset);
         k_place_parents<<<grid_for(lay.node_cap, 256, dev.sm_count, 4), 256, 0, stream>>>(blob8, w.state, lay, w.wide_parent);
     }
     k_finalize<<<1, 32, 0, stream>>>(hdr, w.state, n, lay);

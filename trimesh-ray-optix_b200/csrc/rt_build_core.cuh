@@ -78,6 +78,13 @@ RT_HD uint64_t morton63(float cx, float cy, float cz, const float lo[3], const f
     return expand21((uint64_t)fx) | (expand21((uint64_t)fy) << 1) | (expand21((uint64_t)fz) << 2);
 }
 
+// Bits per axis that take part in the ordering.  The sort costs one pass per 8 key bits, and a Morton grid far finer
+// than the triangle density orders nothing the index tie-break of the hierarchy would not order as well: 16 bits
+// per axis (65 536^3 cells, 6 sort passes) up to 2^25 triangles, 10 bits (4 passes) for small meshes, the full 21
+// (8 passes) beyond.  The key is the top 3*B bits of the 63-bit code, right-aligned.
+RT_HD int morton_axis_bits(int64_t n) { return n > ((int64_t)1 << 25) ? 21 : (n > ((int64_t)1 << 14) ? 16 : 10); }
+RT_HD int morton_sort_passes(int64_t n) { return (3 * morton_axis_bits(n) + 7) / 8 + ((3 * morton_axis_bits(n) + 7) / 8) % 2; }   // even
+
 // ------------------------------------------------------------------ Karras 2012 hierarchy
 #if defined(__CUDA_ARCH__)
 RT_HD int clz64(uint64_t x) { return __clzll((long long)x); }
@@ -187,6 +194,9 @@ RT_HD uint32_t quant_exponent(float ext) {
 struct CollapseOut {
     uint8_t* nodes;          // Node8 array (80 B each)
     uint8_t* tris;           // TriRecord array (48 B each)
+    uint32_t* tri_pos;       // [n] sorted position of the triangle that record i will hold (filled by the collapse, consumed by
+                             // fill_tri_record): a compact array, so a node writes its ~6 positions into one or two sectors
+                             // instead of one 4-byte word into each 48-byte record (a partial-sector write per triangle)
     uint32_t* wide_src;      // binary reference expanded by each wide node
     uint32_t* parent;        // (parent node << 3) | slot of each wide node, 0xffffffff for the root (refit)
     uint32_t* node_count;    // atomic allocators
@@ -302,11 +312,10 @@ RT_HD void write_tri_record(uint8_t* tris, uint32_t slot, uint32_t prim, const f
     *reinterpret_cast<TriRecord*>(tris + (size_t)slot * 48u) = tr;
 }
 
-// second half of the collapse: record `slot` holds a sorted position; resolve it to the face and write the record
-RT_HD void fill_tri_record(uint8_t* tris, uint32_t slot, const uint32_t* __restrict__ sorted_prim,
+// second half of the collapse: tri_pos[slot] is the sorted position of record `slot`; resolve it to the face and write the record
+RT_HD void fill_tri_record(uint8_t* tris, uint32_t slot, const uint32_t* __restrict__ tri_pos, const uint32_t* __restrict__ sorted_prim,
                            const float* __restrict__ verts, int64_t n_verts, const int32_t* __restrict__ faces) {
-    const uint32_t pos = *reinterpret_cast<const uint32_t*>(tris + (size_t)slot * 48u + 12);
-    write_tri_record(tris, slot, sorted_prim[pos], verts, n_verts, faces);
+    write_tri_record(tris, slot, sorted_prim[tri_pos[slot]], verts, n_verts, faces);
 }
 
 // Bottom-up update of one wide node after its children are final (refit): recomputes the slot
@@ -403,9 +412,21 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             ++k;
         }
     }
+    // triangle count and first sorted position of every leaf child.  A leaf child is a single triangle or a binary
+    // node over <= leaf_max of them; when both children of that node are leaves (always, at the default leaf_max of 2)
+    // its range is read off the child references already loaded with its box - no first[] / last[] sector loads
     uint32_t n_inner = 0, n_tris = 0;
+    uint32_t lcount[8], lfirst[8];
+    const uint32_t leaf0 = (uint32_t)(t.n - 1);
     for (int i = 0; i < k; ++i) {
-        if (inner[i]) ++n_inner; else n_tris += bt_count(t, ref[i]);
+        if (inner[i]) { ++n_inner; lcount[i] = 0; lfirst[i] = 0; continue; }
+        if (ref[i] >= leaf0) { lcount[i] = 1; lfirst[i] = ref[i] - leaf0; }
+        else {
+            const uint32_t cl = box_left(cb[i]) & kRefMask, cr = box_right(cb[i]) & kRefMask;
+            if (cl >= leaf0 && cr >= leaf0) { lcount[i] = 2; lfirst[i] = cl - leaf0; }
+            else { lcount[i] = bt_count(t, ref[i]); lfirst[i] = bt_first(t, ref[i]); }
+        }
+        n_tris += lcount[i];
     }
     // greedy slot assignment: child i goes to the free slot whose octant direction agrees
     // best with (child centre - node centre); traversal visits slots in ray-octant order.
@@ -446,15 +467,14 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
             }
             ++rel;
         } else {
-            const uint32_t cnt = bt_count(t, ref[i]);
+            const uint32_t cnt = lcount[i];
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             trimask |= unary << (3 * s);
-            const uint32_t f0 = bt_first(t, ref[i]);
-            // only the SORTED POSITION of each triangle is recorded here (in the record's prim field); the
-            // dependent gathers position -> face -> vertices run afterwards in a fully parallel pass
-            // (fill_tri_record), not serially inside this node's thread
-            for (uint32_t j = 0; j < cnt; ++j)
-                *reinterpret_cast<uint32_t*>(o.tris + (size_t)(tri_base + toff + j) * 48u + 12) = f0 + j;
+            const uint32_t f0 = lfirst[i];
+            // only the SORTED POSITION of each triangle is recorded here (in tri_pos); the dependent gathers
+            // position -> face -> vertices run afterwards in a fully parallel pass (fill_tri_record), not serially
+            // inside this node's thread
+            for (uint32_t j = 0; j < cnt; ++j) o.tri_pos[tri_base + toff + j] = f0 + j;
             toff += cnt;
         }
     }

@@ -235,9 +235,11 @@ __global__ void __launch_bounds__(kThreads) k_onesweep_pass(const uint64_t* __re
 }
 
 // Sorts (keys, vals) in place; `ws` must hold workspace_bytes(n).  All launches go to `stream`.
+// `passes` (even, <= kPasses): only the low 8 * passes key bits are sorted on - the caller guarantees the rest is zero.
 inline cudaError_t sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, void* ws, int sm_count,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int passes = kPasses) {
     if (n <= 1) return cudaSuccess;
+    if (passes < 2 || passes > kPasses || (passes & 1)) return cudaErrorInvalidValue;
     Workspace w = carve(ws, n);
     cudaError_t e = cudaMemsetAsync(w.hist, 0, zero_bytes(n), stream);
     if (e != cudaSuccess) return e;
@@ -253,13 +255,13 @@ inline cudaError_t sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, void* w
     if (e != cudaSuccess) return e;
     uint64_t* kin = keys; uint32_t* vin = vals;
     uint64_t* kout = w.keys_alt; uint32_t* vout = w.vals_alt;
-    for (int p = 0; p < kPasses; ++p) {
+    for (int p = 0; p < passes; ++p) {
         k_onesweep_pass<<<(unsigned)w.n_tiles, kThreads, sizeof(PassSmem), stream>>>(
             kin, vin, kout, vout, n, p, w.hist, w.tile_counter + p, w.status + (size_t)p * w.n_tiles * kRadix);
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
-    // kPasses is even: the result is back in (keys, vals)
+    // `passes` is even: the result is back in (keys, vals)
     return cudaGetLastError();
 }
 
