@@ -231,9 +231,9 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, 
                                                const uint32_t* __restrict__ parent, uint32_t* __restrict__ flags,
                                                BBox* __restrict__ box, uint32_t leaf_max) {
     __shared__ uint32_t s_flags[kRefitTile];
-    const int64_t tiles = (n + kRefitTile - 1) / kRefitTile;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t a = tile * kRefitTile;
+    {
+        const int64_t tile = blockIdx.x;                                      // one tile per CTA: no barrier at a tile's end,
+        const int64_t a = tile * kRefitTile;                                  // the block scheduler balances uneven climbs
         const int64_t b = (a + kRefitTile < n ? a + kRefitTile : n) - 1;      // leaves [a, b]
         for (int i = threadIdx.x; i < kRefitTile; i += blockDim.x) s_flags[i] = 0u;
         __syncthreads();
@@ -273,7 +273,6 @@ __global__ void __launch_bounds__(256) k_refit(const float* __restrict__ verts, 
                 cur = parent[cur];
             }
         }
-        __syncthreads();
     }
 }
 
@@ -414,7 +413,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         k_morton<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state, w.keys, w.vals);
         RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream, morton_sort_passes(n)));
         if (n > 1) k_karras<<<g, 256, 0, stream>>>(w.keys, n, w.left, w.right, w.first, w.last, w.parent);
-        k_refit<<<grid_for((n + kRefitTile - 1) / kRefitTile * 256, 256, dev.sm_count, 8), 256, 0, stream>>>(
+        k_refit<<<(unsigned)((n + kRefitTile - 1) / kRefitTile), 256, 0, stream>>>(
             vertices, n_verts, faces, n, w.vals, w.left, w.right, w.first, w.last, w.parent, w.flags, w.box,
             (uint32_t)leaf_tris_setting());
 

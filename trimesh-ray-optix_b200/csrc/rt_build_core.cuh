@@ -94,41 +94,51 @@ RT_HD int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
 RT_HD int clz32u(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #endif
 
-// length of the common prefix of keys i and j (index as tie-break); -1 when j is out of range
-RT_HD int karras_delta(const uint64_t* __restrict__ keys, int64_t n, int64_t i, int64_t j) {
+// length of the common prefix of keys i and j (index as tie-break); -1 when j is out of range.
+// Idx = int32_t for n <= 2^29 (every probe index i + 2*range stays below 2^31): the searches are index arithmetic,
+// and 32-bit indices halve their instruction count on the GPU; int64_t beyond.
+template <class Idx>
+RT_HD int karras_delta(const uint64_t* __restrict__ keys, Idx n, Idx i, uint64_t key_i, Idx j) {
     if (j < 0 || j >= n) return -1;
-    const uint64_t a = keys[i], b = keys[j];
-    if (a == b) return 64 + clz32u((uint32_t)i ^ (uint32_t)j);
-    return clz64(a ^ b);
+    const uint64_t b = keys[j];
+    if (key_i == b) return 64 + clz32u((uint32_t)i ^ (uint32_t)j);
+    return clz64(key_i ^ b);
 }
 
 // Node references: internal node k -> k (0..n-2); leaf at sorted position k -> (n-1) + k.
 struct KarrasNode { uint32_t left, right, first, last; };
 
-RT_HD KarrasNode karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i) {
-    const int dl = karras_delta(keys, n, i, i - 1), dr = karras_delta(keys, n, i, i + 1);
-    const int64_t d = dr > dl ? 1 : -1;
+template <class Idx>
+RT_HD KarrasNode karras_node_t(const uint64_t* __restrict__ keys, Idx n, Idx i) {
+    const uint64_t ki = keys[i];
+    const int dl = karras_delta<Idx>(keys, n, i, ki, i - 1), dr = karras_delta<Idx>(keys, n, i, ki, i + 1);
+    const Idx d = dr > dl ? 1 : -1;
     const int dmin = dr > dl ? dl : dr;
-    int64_t lmax = 2;
-    while (karras_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-    int64_t l = 0;
-    for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
-        if (karras_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    const int64_t j = i + l * d;
-    const int dnode = karras_delta(keys, n, i, j);
-    int64_t s = 0;
-    for (int64_t t = (l + 1) >> 1;; t = (t + 1) >> 1) {
-        if (karras_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    Idx lmax = 2;
+    while (karras_delta<Idx>(keys, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    Idx l = 0;
+    for (Idx t = lmax >> 1; t >= 1; t >>= 1)
+        if (karras_delta<Idx>(keys, n, i, ki, i + (l + t) * d) > dmin) l += t;
+    const Idx j = i + l * d;
+    const int dnode = karras_delta<Idx>(keys, n, i, ki, j);
+    Idx s = 0;
+    for (Idx t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (karras_delta<Idx>(keys, n, i, ki, i + (s + t) * d) > dnode) s += t;
         if (t <= 1) break;
     }
-    const int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
-    const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    const Idx gamma = i + s * d + (d < 0 ? -1 : 0);
+    const Idx lo = i < j ? i : j, hi = i < j ? j : i;
     KarrasNode k;
     k.left = (uint32_t)(lo == gamma ? (n - 1) + gamma : gamma);
     k.right = (uint32_t)(hi == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
     k.first = (uint32_t)lo;
     k.last = (uint32_t)hi;
     return k;
+}
+
+RT_HD KarrasNode karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i) {
+    if (n <= ((int64_t)1 << 29)) return karras_node_t<int32_t>(keys, (int32_t)n, (int32_t)i);
+    return karras_node_t<int64_t>(keys, n, i);
 }
 
 // ------------------------------------------------------------------ collapse to BVH8
@@ -249,7 +259,8 @@ inline void alloc_children(const CollapseOut& o, uint32_t n_inner, uint32_t n_tr
 // Quantisation of the child boxes of one wide node: frame (p, 2^e) from the node box, 8-bit planes
 // rounded outwards and verified in binary64 against the exact decode p + q * 2^e.  Shared by the
 // builder (collapse) and the refit path.  Absent slots get an inverted box.
-RT_HD void quantise_slots(const BBox& nb, const BBox slot_box[8], uint32_t present, Node8& nd) {
+// slot s holds boxes[idx_of_slot[s]] (present bit s set) or nothing
+RT_HD void quantise_slots(const BBox& nb, const BBox* boxes, const int idx_of_slot[8], uint32_t present, Node8& nd) {
     const float p[3] = {nb.lx, nb.ly, nb.lz};
     const float hi3[3] = {nb.hx, nb.hy, nb.hz};
     uint32_t e[3];
@@ -261,7 +272,8 @@ RT_HD void quantise_slots(const BBox& nb, const BBox slot_box[8], uint32_t prese
             bool ok = true;
             for (int s = 0; s < 8; ++s) {
                 if (!((present >> s) & 1u)) continue;
-                const float ch = a == 0 ? slot_box[s].hx : (a == 1 ? slot_box[s].hy : slot_box[s].hz);
+                const BBox& sb = boxes[idx_of_slot[s]];
+                const float ch = a == 0 ? sb.hx : (a == 1 ? sb.hy : sb.hz);
                 if ((double)p[a] + 255.0 * sc < (double)ch) { ok = false; break; }
             }
             if (ok || e[a] >= 254u) break;
@@ -277,9 +289,10 @@ RT_HD void quantise_slots(const BBox& nb, const BBox slot_box[8], uint32_t prese
             continue;
         }
         uint8_t ql[3], qh[3];
+        const BBox sb = boxes[idx_of_slot[s]];
         for (int a = 0; a < 3; ++a) {
-            const float cl = a == 0 ? slot_box[s].lx : (a == 1 ? slot_box[s].ly : slot_box[s].lz);
-            const float ch = a == 0 ? slot_box[s].hx : (a == 1 ? slot_box[s].hy : slot_box[s].hz);
+            const float cl = a == 0 ? sb.lx : (a == 1 ? sb.ly : sb.lz);
+            const float ch = a == 0 ? sb.hx : (a == 1 ? sb.hy : sb.hz);
             const double sc = (double)exp2_biased(e[a]);
             const double isc = (double)exp2_biased(254u - e[a]);   // exact 1/sc (power of two): no double division
             double fl = floor(((double)cl - (double)p[a]) * isc);
@@ -324,9 +337,11 @@ RT_HD void fill_tri_record(uint8_t* tris, uint32_t slot, const uint32_t* __restr
 RT_HD BBox refit_node(uint8_t* nodes, const uint8_t* tris, uint32_t w, const BBox* child_box_of_node) {
     Node8 nd = *reinterpret_cast<const Node8*>(nodes + (size_t)w * 80u);
     BBox slot_box[8];
+    int idx_of_slot[8];
     BBox nb; nb.lx = nb.ly = nb.lz = INFINITY; nb.hx = nb.hy = nb.hz = -INFINITY; nb.pad0 = nb.pad1 = 0.f;
     uint32_t present = 0, rel = 0, toff = 0;
     for (int s = 0; s < 8; ++s) {
+        idx_of_slot[s] = s;
         const bool inner = (nd.imask >> s) & 1u;
         const uint32_t un = (nd.trimask >> (3 * s)) & 7u;
         if (inner) {
@@ -348,7 +363,7 @@ RT_HD BBox refit_node(uint8_t* nodes, const uint8_t* tris, uint32_t w, const BBo
         nb = bbox_union(nb, slot_box[s]);
     }
     if (present == 0u) { nb.lx = nb.ly = nb.lz = 0.f; nb.hx = nb.hy = nb.hz = 0.f; }
-    quantise_slots(nb, slot_box, present, nd);
+    quantise_slots(nb, slot_box, idx_of_slot, present, nd);
     *reinterpret_cast<Node8*>(nodes + (size_t)w * 80u) = nd;
     return nb;
 }
@@ -373,7 +388,8 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     uint32_t ref[8];
     float area[8];
     bool inner[8];
-    BBox cb[8];
+    BBox cb[8];        // (tried: in shared memory, one column per thread, to shrink the 700-byte stack frame - the kernel
+                       //  moves 4 GB of DRAM at 16.8 M triangles - but 80 registers / 32 KB cost more occupancy than it saved)
     int k = 0;
     const uint32_t src = load_cg_u32(&o.wide_src[w]);
     const BBox nb = t.box[src];
@@ -447,12 +463,11 @@ RT_HD void collapse_node(const BinaryTree& t, const CollapseOut& o, uint32_t w, 
     uint32_t child_base, tri_base;
     alloc_children(o, n_inner, n_tris, child_base, tri_base);
 
-    BBox slot_box[8];
     uint32_t present = 0;
     for (int s = 0; s < 8; ++s)
-        if (child_in_slot[s] >= 0) { slot_box[s] = cb[child_in_slot[s]]; present |= 1u << s; }
+        if (child_in_slot[s] >= 0) present |= 1u << s;
     Node8 nd;
-    quantise_slots(nb, slot_box, present, nd);
+    quantise_slots(nb, cb, child_in_slot, present, nd);
     nd.child_base = child_base;
     nd.tri_base = tri_base;
     uint32_t imask = 0, trimask = 0, rel = 0, toff = 0;
