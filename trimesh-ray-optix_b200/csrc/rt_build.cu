@@ -411,18 +411,20 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         const int g = grid_for(n, 256, dev.sm_count, 8);
         k_scene_bounds<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state);
         k_morton<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, w.state, w.keys, w.vals);
-        RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream, morton_sort_passes(n)));
-        if (n > 1) k_karras<<<g, 256, 0, stream>>>(w.keys, n, w.left, w.right, w.first, w.last, w.parent);
+        // an odd number of passes leaves the sorted keys / triangle ids in the sort's alternate buffers: use them where they are
+        uint64_t* skeys = w.keys; uint32_t* svals = w.vals;
+        RT_CUDA_TRY(sort::sort_pairs(w.keys, w.vals, n, w.sort_ws, dev.sm_count, stream, morton_sort_passes(n), &skeys, &svals));
+        if (n > 1) k_karras<<<g, 256, 0, stream>>>(skeys, n, w.left, w.right, w.first, w.last, w.parent);
         k_refit<<<(unsigned)((n + kRefitTile - 1) / kRefitTile), 256, 0, stream>>>(
-            vertices, n_verts, faces, n, w.vals, w.left, w.right, w.first, w.last, w.parent, w.flags, w.box,
+            vertices, n_verts, faces, n, svals, w.left, w.right, w.first, w.last, w.parent, w.flags, w.box,
             (uint32_t)leaf_tris_setting());
 
         BinaryTree t;
         t.n = n; t.left = w.left; t.right = w.right; t.first = w.first; t.last = w.last; t.box = w.box;
-        t.sorted_prim = w.vals; t.leaf_max = leaf_tris_setting(); t.flagged = 1;
+        t.sorted_prim = svals; t.leaf_max = leaf_tris_setting(); t.flagged = 1;
         CollapseOut o;
         o.nodes = blob8 + lay.nodes_offset; o.tris = blob8 + lay.tris_offset; o.wide_src = w.wide_src;
-        o.tri_pos = reinterpret_cast<uint32_t*>(w.keys);      // the sorted keys are dead once the hierarchy exists (8n bytes, n words needed)
+        o.tri_pos = reinterpret_cast<uint32_t*>(skeys);       // the sorted keys are dead once the hierarchy exists (8n bytes, n words needed)
         o.parent = w.wide_parent;
         o.node_count = &w.state->node_count; o.tri_count = &w.state->tri_count; o.node_cap = lay.node_cap;
         int per_sm = 0;
@@ -434,7 +436,7 @@ extern "C" int rt_bvh_build(const float* vertices, int64_t n_verts, const int32_
         BuildState* stp = w.state;
         void* args[] = {&t, &o, (void*)&vertices, (void*)&n_verts, (void*)&faces, &stp};
         RT_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(cgrid), dim3(128), args, 0, stream));
-        k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, o.tri_pos, w.vals, blob8 + lay.tris_offset);
+        k_fill_tris<<<g, 256, 0, stream>>>(vertices, n_verts, faces, n, o.tri_pos, svals, blob8 + lay.tris_offset);
         k_place_parents<<<grid_for(lay.node_cap, 256, dev.sm_count, 4), 256, 0, stream>>>(blob8, w.state, lay, w.wide_parent);
     }
     k_finalize<<<1, 32, 0, stream>>>(hdr, w.state, n, lay);

@@ -79,11 +79,17 @@ RT_HD uint64_t morton63(float cx, float cy, float cz, const float lo[3], const f
 }
 
 // Bits per axis that take part in the ordering.  The sort costs one pass per 8 key bits, and a Morton grid far finer
-// than the triangle density orders nothing the index tie-break of the hierarchy would not order as well: 16 bits
-// per axis (65 536^3 cells, 6 sort passes) up to 2^25 triangles, 10 bits (4 passes) for small meshes, the full 21
-// (8 passes) beyond.  The key is the top 3*B bits of the 63-bit code, right-aligned.
-RT_HD int morton_axis_bits(int64_t n) { return n > ((int64_t)1 << 25) ? 21 : (n > ((int64_t)1 << 14) ? 16 : 10); }
-RT_HD int morton_sort_passes(int64_t n) { return (3 * morton_axis_bits(n) + 7) / 8 + ((3 * morton_axis_bits(n) + 7) / 8) % 2; }   // even
+// than the triangle density orders nothing the index tie-break of the hierarchy would not order as well:
+// RT_MORTON_BITS_MID bits per axis up to 2^24 triangles (13 -> 39 key bits -> 5 sort passes; 8192 cells per axis are
+// still >= 2 per triangle edge of a 16.8 M-triangle surface), 10 bits (4 passes) for small meshes, 16 (6 passes) up to
+// 2^25 triangles and the full 21 (8 passes) beyond.  The key is the top 3*B bits of the 63-bit code, right-aligned.
+#ifndef RT_MORTON_BITS_MID
+#define RT_MORTON_BITS_MID 13
+#endif
+RT_HD int morton_axis_bits(int64_t n) {
+    return n > ((int64_t)1 << 25) ? 21 : (n > ((int64_t)1 << 24) ? 16 : (n > ((int64_t)1 << 14) ? RT_MORTON_BITS_MID : 10));
+}
+RT_HD int morton_sort_passes(int64_t n) { return (3 * morton_axis_bits(n) + 7) / 8; }
 
 // ------------------------------------------------------------------ Karras 2012 hierarchy
 #if defined(__CUDA_ARCH__)

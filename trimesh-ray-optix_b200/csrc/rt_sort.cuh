@@ -235,11 +235,16 @@ __global__ void __launch_bounds__(kThreads) k_onesweep_pass(const uint64_t* __re
 }
 
 // Sorts (keys, vals) in place; `ws` must hold workspace_bytes(n).  All launches go to `stream`.
-// `passes` (even, <= kPasses): only the low 8 * passes key bits are sorted on - the caller guarantees the rest is zero.
+// `passes` (<= kPasses): only the low 8 * passes key bits are sorted on - the caller guarantees the rest is zero.  With an odd
+// number of passes the sorted data ends in the workspace's alternate buffers; `keys_out` / `vals_out` (optional) say where
+// it is, and an odd count without them is refused.
 inline cudaError_t sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, void* ws, int sm_count,
-                              cudaStream_t stream, int passes = kPasses) {
+                              cudaStream_t stream, int passes = kPasses, uint64_t** keys_out = nullptr,
+                              uint32_t** vals_out = nullptr) {
+    if (keys_out) *keys_out = keys;
+    if (vals_out) *vals_out = vals;
     if (n <= 1) return cudaSuccess;
-    if (passes < 2 || passes > kPasses || (passes & 1)) return cudaErrorInvalidValue;
+    if (passes < 1 || passes > kPasses || ((passes & 1) && !(keys_out && vals_out))) return cudaErrorInvalidValue;
     Workspace w = carve(ws, n);
     cudaError_t e = cudaMemsetAsync(w.hist, 0, zero_bytes(n), stream);
     if (e != cudaSuccess) return e;
@@ -261,7 +266,9 @@ inline cudaError_t sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, void* w
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
-    // `passes` is even: the result is back in (keys, vals)
+    // after the last swap (kin, vin) is where the sorted data lives: (keys, vals) for an even number of passes
+    if (keys_out) *keys_out = kin;
+    if (vals_out) *vals_out = vin;
     return cudaGetLastError();
 }
 
