@@ -188,9 +188,23 @@ def set_knobs(**kw) -> dict:
     return old
 
 
+_opts_cache: dict = {}
+
+
 def trace_opts(accel=None, ray_first: int = 0, ray_count: int = -1, scratch_zeroed: bool = True) -> TraceOpts:
     """rt_trace_opts of one call: the accel's tmax (default 1e7 = the reference's hard-coded value), the ray window,
-    and the experiment knobs."""
+    and the experiment knobs.  The whole-batch form is cached per (tmax, knobs)."""
+    if ray_first == 0 and ray_count < 0 and scratch_zeroed:
+        tm = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
+        key = (tm, _KNOBS["schedule"], _KNOBS["refill_threshold"], _KNOBS["tri_threshold"], _KNOBS["grid_div"])
+        o = _opts_cache.get(key)
+        if o is None:
+            o = _opts_cache[key] = _trace_opts(accel, 0, -1, True)
+        return o
+    return _trace_opts(accel, ray_first, ray_count, scratch_zeroed)
+
+
+def _trace_opts(accel, ray_first: int, ray_count: int, scratch_zeroed: bool) -> TraceOpts:
     o = TraceOpts()
     o.tmax = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
     o.schedule = _KNOBS["schedule"]
@@ -207,17 +221,34 @@ def _stream(device) -> int:
 _scratch_cache: dict = {}
 
 
-def _scratch(device) -> torch.Tensor:
+def _scratch(device, stream: int | None = None) -> torch.Tensor:
     """RT_TRACE_SCRATCH_BYTES of zeroed device memory private to (device, current stream).  Every launch leaves its
     scratch zeroed again (the last CTA resets it), so with RT_OPT_SCRATCH_ZEROED a trace call is exactly one kernel
     launch; launches that share a scratch are ordered by their stream."""
-    dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev) if stream is None else stream)
     t = _scratch_cache.get(key)
     if t is None:
         t = torch.zeros(TRACE_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
         _scratch_cache[key] = t
     return t
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager costs ~3 us per call)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
 
 
 def _ptr(t: torch.Tensor | None):
@@ -239,9 +270,26 @@ def tensor_input_check(*ts: torch.Tensor):
             raise ValueError(f"input tensors must be float32 (got {t.dtype})")
 
 
+_desc_cache = (None, None)      # (key, value), replaced as ONE object so that threads never pair a key with another call's value
+
+
 def make_ray_desc(origins: torch.Tensor, dirs: torch.Tensor | None) -> Tuple[RayDesc, tuple]:
     """fillArray of the reference (ray.cpp:151-159): right-align shape/strides into 4 slots.
-    The batch shape is that of `origins` (ray.cpp:177-179)."""
+    The batch shape is that of `origins` (ray.cpp:177-179).  A call with the same addresses, shapes and strides as the
+    previous one (a render loop) reuses its descriptor: filling a ctypes struct costs more than the rest of the host side."""
+    key = (origins.data_ptr(), origins.shape, origins.stride(), origins.device,
+           None if dirs is None else (dirs.data_ptr(), dirs.shape, dirs.stride(), dirs.device))
+    global _desc_cache
+    cached = _desc_cache
+    if cached[0] == key:
+        return cached[1]
+    val = _make_ray_desc(origins, dirs)
+    if val[0]._keepalive is None:          # reshaped copies must not outlive their call through the cache
+        _desc_cache = (key, val)
+    return val
+
+
+def _make_ray_desc(origins: torch.Tensor, dirs: torch.Tensor | None) -> Tuple[RayDesc, tuple]:
     if origins.dim() < 1 or origins.shape[-1] != 3:
         raise ValueError(f"origins must have shape [*b, 3], got {tuple(origins.shape)}")
     if dirs is not None and tuple(dirs.shape) != tuple(origins.shape):
@@ -426,10 +474,11 @@ def intersects_any(accel_structure, origins: torch.Tensor, dirs: torch.Tensor) -
     blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty(batch, dtype=torch.bool, device=dev)
+        st = _stream(dev)
         _check(get_module().rt_trace_any(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
-                                         _ptr(_scratch(dev)), _stream(dev)), "rt_trace_any")
+                                         _ptr(_scratch(dev, st)), st), "rt_trace_any")
     return out
 
 
@@ -439,10 +488,11 @@ def intersects_first(accel_structure, origins: torch.Tensor, dirs: torch.Tensor)
     blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty(batch, dtype=torch.int32, device=dev)
+        st = _stream(dev)
         _check(get_module().rt_trace_first(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
-                                           _ptr(_scratch(dev)), _stream(dev)), "rt_trace_first")
+                                           _ptr(_scratch(dev, st)), st), "rt_trace_first")
     return out
 
 
@@ -456,7 +506,7 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
     if ray_first != 0 or ray_count >= 0:
         batch = (_window(rd.nray, ray_first, ray_count),)
     dev = origins.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         hit = torch.empty(batch, dtype=torch.bool, device=dev)
         front = torch.empty(batch, dtype=torch.bool, device=dev)
         tri = torch.empty(batch, dtype=torch.int32, device=dev)
@@ -464,9 +514,10 @@ def intersects_closest(accel_structure, origins: torch.Tensor, dirs: torch.Tenso
         uv = torch.empty((*batch, 2), dtype=torch.float32, device=dev)
         if hit.numel() == 0:
             return hit, front, tri, loc, uv
+        st = _stream(dev)
         _check(get_module().rt_trace_closest(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure, ray_first, ray_count)),
-                                             _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc), _ptr(uv), _ptr(_scratch(dev)),
-                                             _stream(dev)), "rt_trace_closest")
+                                             _ptr(hit), _ptr(front), _ptr(tri), _ptr(loc), _ptr(uv), _ptr(_scratch(dev, st)),
+                                             st), "rt_trace_closest")
     return hit, front, tri, loc, uv
 
 
@@ -622,10 +673,11 @@ def intersects_count(accel_structure, origins: torch.Tensor, dirs: torch.Tensor)
     blob = _blob_of(accel_structure, origins.device)
     rd, batch = make_ray_desc(origins, dirs)
     dev = origins.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty(batch, dtype=torch.int32, device=dev)
+        st = _stream(dev)
         _check(get_module().rt_trace_count(_ptr(blob), C.byref(rd), C.byref(trace_opts(accel_structure)), _ptr(out),
-                                           _ptr(_scratch(dev)), _stream(dev)), "rt_trace_count")
+                                           _ptr(_scratch(dev, st)), st), "rt_trace_count")
     return out
 
 
@@ -696,6 +748,7 @@ def contains_parity(accel_structure, points: torch.Tensor, direction, aabb_lo, a
         flags = torch.empty(2, dtype=torch.int32, device=dev)
         opts = trace_opts(accel_structure)
         if stop_when_broken:
+            opts = _trace_opts(accel_structure, 0, -1, True)       # a private copy: the whole-batch form is a shared cached object
             opts.flags |= OPT_STOP_WHEN_BROKEN
         _check(get_module().rt_contains_parity(_ptr(blob), C.byref(rd), C.byref(opts), d3, lo3, hi3,
                                                _ptr(active), _ptr(contain), _ptr(broken), _ptr(flags), _ptr(_scratch(dev)),
