@@ -125,6 +125,9 @@ typedef struct rt_blob_header {
                                       known to be 1; contain / broken entries are then unspecified for the points it skipped.
                                       For callers that discard the per-point results in that case, like the retry of
                                       ray_optix.py:272-279 (a retry with broken points yields all False for the subset). */
+#define RT_OPT_NO_LANE_SHARING 4u  /* cooperative schedules: lanes of a warp that can draw no more rays normally take over
+                                      part of a neighbour's traversal stack (results are identical either way); this
+                                      switches that off (experiments) */
 typedef struct rt_trace_opts {
     float tmax;
     int32_t schedule;

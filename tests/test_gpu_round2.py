@@ -75,6 +75,42 @@ def test_all_schedules_give_identical_results(cuda_device, scene):
     check_closest_vs_mirror(base["closest"], om, flat(o), flat(d))
 
 
+@pytest.mark.parametrize("n_rays", [1, 33, 5_000, 200_000])
+def test_lane_sharing_in_the_launch_tail_changes_no_bit(cuda_device, n_rays):
+    """Lanes of a warp that can draw no more rays walk parts of their neighbours' traversal stacks (rt_trace_coop.cuh,
+    step 1b).  Small launches on a soup are nearly all tail: with sharing on (default), off
+    (RT_OPT_NO_LANE_SHARING) and under the per-lane round-1 kernel every query must give the same bits, and the
+    closest hit must equal the oracle's."""
+    v, f = synth.triangle_soup(30_000, sigma=0.03, seed=11)
+    o, d = synth.random_rays(n_rays, seed=12, device=cuda_device, box=True)
+    pts = o[: min(n_rays, 20_000)].contiguous()
+    r = make(v, f)
+    res = []
+    for kw in (dict(), dict(no_lane_sharing=1), dict(schedule=hops.SCHED_COOP_COHERENT), dict(schedule=hops.SCHED_DIRECT)):
+        with knobs(**kw):
+            got = dict(closest=closest_to_numpy(r.intersects_closest(o, d)), first=r.intersects_first(o, d).cpu().numpy(),
+                       any=r.intersects_any(o, d).cpu().numpy(), count=r.intersects_count(o, d).cpu().numpy())
+            c, b, fl = r.contains_parity(pts, [0.3, 0.5, 0.8])
+            got["contains"] = (c.cpu().numpy(), b.cpu().numpy(), fl.cpu().numpy())
+            loc, ray_idx, tri_idx = r.intersects_location(o, d)
+            key = np.lexsort((tri_idx.cpu().numpy(), ray_idx.cpu().numpy()))
+            got["location"] = (ray_idx.cpu().numpy()[key], tri_idx.cpu().numpy()[key], loc.cpu().numpy()[key])
+        res.append(got)
+    cnt = res[0]["count"]
+    for got in res[1:]:
+        for k in got["closest"]:
+            assert_bits_equal(got["closest"][k], res[0]["closest"][k], f"closest.{k}")
+        for k in ("first", "any", "count"):
+            assert np.array_equal(got[k], res[0][k]), k
+        for a, b_ in zip(got["contains"], res[0]["contains"]):
+            assert np.array_equal(a, b_), "contains"
+        if cnt.max(initial=0) <= 8:          # beyond max_hits the recorded subset is test order (reference: traversal order)
+            for a, b_ in zip(got["location"], res[0]["location"]):
+                assert_bits_equal(a, b_, "location")
+    om = oracle.OracleMesh(v, f)
+    check_closest_vs_mirror(res[0]["closest"], om, flat(o), flat(d))
+
+
 def test_trace_stats_direct_equals_host_simulation_and_coop_never_skips(cuda_device):
     v, f = synth.icosphere(4)
     r = make(v, f)

@@ -22,6 +22,9 @@ for sub, soup in ((3, False), (0, True)):
         r.contains_points(o)
         hops.set_knobs(**old)
     hops.intersects_closest(r.as_wrapper, o, d, 100, 1000)           # ray window
+    old = hops.set_knobs(no_lane_sharing=1)
+    r.intersects_closest(o, d); r.intersects_count(o, d)
+    hops.set_knobs(**old)
     hops.intersects_location(r.as_wrapper, o, d, 8, staging_bytes=1000 * 8 * 16)
     r.contains_points(o)
     r.refit(torch.from_numpy(v * 1.1))

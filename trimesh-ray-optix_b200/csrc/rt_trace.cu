@@ -54,6 +54,7 @@ struct TraceParams {
     float dir[3], aabb_lo[3], aabb_hi[3];
     const uint8_t* active;       // optional per-point mask (may alias `broken`)
     int stop_on_broken;          // RT_OPT_STOP_WHEN_BROKEN
+    int share_lanes;             // !RT_OPT_NO_LANE_SHARING
     uint8_t* contain;
     uint8_t* broken;
     int32_t* flags;
@@ -536,6 +537,7 @@ static int check_rays(const char* fn, const rt_ray_desc* rays, bool need_dirs) {
 
 // resident CTAs per SM of every kernel variant, per device (filled on first use; benign race: same value)
 constexpr int kMaxDevices = 64;
+constexpr int64_t kShareMaxRaysCoherentClosest = 1 << 20;   // coherent closest hit: launches up to this many rays share work in the tail
 static int g_per_sm[kMaxDevices][5][2][8];
 
 template <int MODE>
@@ -552,8 +554,8 @@ static int occupancy(int sched, int* per_sm) {
             return (int)cudaErrorInvalidValue;
         default:
             if (sched == RT_SCHED_COOP_COHERENT)
-                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, false>, kTraceThreads, 0);
-            return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, true>, kTraceThreads, 0);
+                return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, false, true>, kTraceThreads, 0);
+            return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_trace_coop<MODE, STATS, true, true>, kTraceThreads, 0);
     }
 }
 
@@ -587,6 +589,7 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     }
     p.tmax = o.tmax > 0.0f ? o.tmax : RT_TMAX_DEFAULT;     // NaN and <= 0 select the reference's 1e7
     p.stop_on_broken = (MODE == kContains && (o.flags & RT_OPT_STOP_WHEN_BROKEN)) ? 1 : 0;
+    p.share_lanes = (o.flags & RT_OPT_NO_LANE_SHARING) ? 0 : 1;
     p.byte_magic = kByteMagic;
     p.ray_counter = reinterpret_cast<unsigned long long*>(scratch);
     if (!(o.flags & RT_OPT_SCRATCH_ZEROED)) RT_CUDA_TRY(cudaMemsetAsync(scratch, 0, RT_TRACE_SCRATCH_BYTES, stream));
@@ -630,8 +633,17 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
             if constexpr (kHasSlots<MODE>) k_trace_slots<MODE, STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
             break;
         default:
-            if (sched == RT_SCHED_COOP_COHERENT) k_trace_coop<MODE, STATS, false><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
-            else k_trace_coop<MODE, STATS, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            // Work sharing between the lanes of a draining warp (rt_trace_coop.cuh, step 1b) is compiled into every
+            // cooperative kernel; coherent closest hit exists a second time without it, for big launches: there the
+            // tail is a small part of the launch and the leaner loop is worth 1-3 % (profiles/r2_sweeps.md "p").
+            if (sched == RT_SCHED_COOP_COHERENT) {
+                if (MODE == kClosest && !STATS && count > kShareMaxRaysCoherentClosest)
+                    k_trace_coop<MODE, STATS, false, MODE != kClosest || STATS><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+                else
+                    k_trace_coop<MODE, STATS, false, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            } else {
+                k_trace_coop<MODE, STATS, true, true><<<(unsigned)grid, kTraceThreads, 0, stream>>>(p);
+            }
     }
     RT_CUDA_TRY(cudaGetLastError());
     return RT_OK;

@@ -18,6 +18,10 @@
 //     batch, and parks them in shared memory; retiring a ray is then a plain copy (k_trace re-fetches
 //     and re-tests the winning triangle with the few lanes that retire together).
 //
+//   * once a warp can draw no more rays (the tail of a launch; all of a small launch), lanes without a ray take
+//     over part of a busy neighbour's traversal stack (step 1b, template parameter SHARE): possible because
+//     everything a triangle test or a hit touches is addressed by the ray's shared-memory column, not by the lane.
+//
 // ncu of k_trace on config 2 (profiles/r1_ncu_regions_config2_v4.txt): the in-step triangle test was
 // 27.8 % of all warp instructions at 8.17 of 32 active lanes.  Results are bit-identical to k_trace
 // (tests/test_gpu_parity.py::test_all_schedules_give_identical_results).
@@ -30,14 +34,18 @@ namespace rt {
 #endif
 constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
 constexpr int kTailLanes = 4;          // <= this many lanes with node work: test listed pairs every step
+#ifndef RT_SHARE_TAIL
+#define RT_SHARE_TAIL 1
+#endif
 constexpr int kRayWords = 7;           // resident part of a ray in shared memory: S(3), permuted origin(3), kzf
 
 // POOL = incoherent batches: rays are prepared 32 at a time into a shared-memory pool and lanes re-fill early;
 // otherwise lanes re-fill late and set their ray up in place (coherent batches).
-template <int MODE, bool STATS, bool POOL>
+template <int MODE, bool STATS, bool POOL, bool SHARE>
 __global__ void __launch_bounds__(kTraceThreads, (MODE == kClosest && POOL) ? RT_TRACE_MIN_BLOCKS : RT_TRACE_MIN_BLOCKS_LIGHT)
 k_trace_coop(const __grid_constant__ TraceParams p) {
     constexpr bool kKey = MODE == kClosest || MODE == kFirst;
+    constexpr bool kShare = SHARE && RT_SHARE_TAIL;
     __shared__ float s_ray[kRayWords][kTraceThreads];
     __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim
     __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
@@ -70,10 +78,14 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
     int pool_head = 0, pool_count = 0;
     int64_t pool_base = 0;
     uint32_t ty = 0u, tx = 0u, tmask = 0u;      // triangles of this lane's last node step not yet listed
+    // column of the ray this lane walks for: its own, or (work sharing, RT_SHARE_TAIL) a neighbour's - a helper keeps
+    // ~column in r, which it does not need (no extra register in the loop)
+    auto owner_col = [&]() -> int { return r < 0 ? (int)(~r) : mycol; };
     trav_init(tv);
 
     // ---- test every listed pair with the whole warp
-    auto flush = [&]() {
+    auto flush = [&](auto drain_tag) {
+        constexpr bool DRAIN = decltype(drain_tag)::value;
         __syncwarp();
         for (int base = 0; base < n_pend; base += 32) {
             const int i = base + lane;
@@ -130,8 +142,9 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         }
         __syncwarp();
         n_pend = 0; my_pend = 0;
-        if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[mycol] >> 32));
-        if constexpr (MODE == kAny) { if (active && s_cnt[mycol]) { nodes_done = true; ty = 0u; } }   // early exit
+        const int oc = DRAIN ? owner_col() : mycol;
+        if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[oc] >> 32));
+        if constexpr (MODE == kAny) { if (active && s_cnt[oc]) { nodes_done = true; ty = 0u; } }   // early exit
     };
 
     // ---- start ray r on this lane from a prepared set-up
@@ -147,7 +160,12 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         active = true;
     };
 
-    for (;;) {
+    // One iteration of the traversal loop; returns 1 when the warp is finished, 2 to switch to the DRAIN instance.  Instantiated twice: DRAIN = false is
+    // the loop proper; DRAIN = true runs once this warp can draw no more rays and adds work sharing between its lanes
+    // (a separate instance, so that the hot loop's code is exactly what it is without sharing: folding the two cost 3-4 %
+    // on config 2, profiles/r2_sweeps.md "p").
+    auto step = [&](auto drain_tag) -> int {
+        constexpr bool DRAIN = decltype(drain_tag)::value;
         // ---- 1. flush policy (the ONE place pairs are tested), retirement, re-fill
         const unsigned done_mask = __ballot_sync(0xffffffffu, !active || nodes_done);
         const int busy = 32 - __popc(done_mask);
@@ -158,7 +176,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
             bool go = n_pend >= p.tri_threshold || busy <= kTailLanes;
             if (!go && n_pend == kPairCap) go = true;                                                      // list full (triangles may be waiting in ty)
             if (!go && want_refill) go = __any_sync(0xffffffffu, active && nodes_done && my_pend != 0);   // rays wait to retire
-            if (go) flush();
+            if (go) flush(drain_tag);
         }
         if (want_refill) {
             if constexpr (MODE == kContains) {
@@ -170,7 +188,16 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     if (__shfl_sync(0xffffffffu, f, 0)) { exhausted = true; pool_count = 0; }
                 }
             }
-            if (active && nodes_done && my_pend == 0 && ty == 0u) {
+            bool retire = active && nodes_done && my_pend == 0 && ty == 0u;
+            if constexpr (DRAIN) {
+                // work sharing (below): a helper that has listed everything simply becomes idle; a ray retires once no
+                // helper still walks or holds unlisted triangles for it (the list itself is empty here: the flush above
+                // ran, because no lane has node work left)
+                if (retire && r < 0) { active = false; r = 0; retire = false; }
+                const unsigned helped = __reduce_or_sync(0xffffffffu, (active && r < 0) ? 1u << ((int)(~r) & 31) : 0u);
+                if ((helped >> lane) & 1u) retire = false;
+            }
+            if (retire) {
                 if constexpr (MODE == kClosest || MODE == kFirst) {
                     const unsigned long long best = s_best[mycol];
                     const bool hit = best != key_init;
@@ -304,9 +331,46 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active)) {
-                if (exhausted && pool_count == 0) break;
-                continue;      // every lane drew a masked-out point: draw again
+            if (!__any_sync(0xffffffffu, active)) return (exhausted && pool_count == 0) ? 1 : 0;   // 0: every lane drew a masked-out point, draw again
+            if constexpr (!DRAIN && kShare) { if (exhausted && pool_count == 0 && p.share_lanes) return 2; }
+        }
+
+        // ---- 1b. work sharing once this warp can draw no more rays: a lane without a ray takes the top stack entry (the
+        //          nearest untested sibling group) of a lane that still walks, together with that ray's node-test registers,
+        //          and walks it as a HELPER.  Everything a triangle test or a hit needs is indexed by the ray's shared-memory
+        //          column (s_ray / s_best / s_cnt / s_attr / s_rayidx), pairs carry the owner's column, and the closest hit is
+        //          an order-independent atomicMin, so results do not depend on who walked which subtree; only the owner
+        //          retires the ray.  Cuts the tail of a launch: a silhouette ray's 60 node steps spread over the warp.
+        if constexpr (DRAIN) {
+            if (active && r < 0 && nodes_done && ty == 0u) { active = false; r = 0; }      // helper finished
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            const unsigned rich = __ballot_sync(0xffffffffu, active && !nodes_done && tv.sp > 0);
+            if (idle != 0u && rich != 0u) {
+                const int n_idle = __popc(idle), n_rich = __popc(rich);
+                const int take = n_idle < n_rich ? n_idle : n_rich;
+                uint32_t sgx = 0u, sgy = 0u;
+                if (((rich >> lane) & 1u) && __popc(rich & lt_mask) < take) { --tv.sp; stack.pop(tv.sp, sgx, sgy); }
+                const int my = __popc(idle & lt_mask);
+                const bool get = !active && my < take;
+                const int src = get ? (int)__fns(rich, 0u, my + 1) : lane;
+                sgx = __shfl_sync(0xffffffffu, sgx, src); sgy = __shfl_sync(0xffffffffu, sgy, src);
+                const float hox = __shfl_sync(0xffffffffu, ray.ox, src), hoy = __shfl_sync(0xffffffffu, ray.oy, src),
+                            hoz = __shfl_sync(0xffffffffu, ray.oz, src);
+                const float hix = __shfl_sync(0xffffffffu, ray.idx, src), hiy = __shfl_sync(0xffffffffu, ray.idy, src),
+                            hiz = __shfl_sync(0xffffffffu, ray.idz, src);
+                const uint32_t hoct = __shfl_sync(0xffffffffu, ray.octinv, src);
+                const int hcol = __shfl_sync(0xffffffffu, owner_col(), src);
+                if (get) {
+                    ray.ox = hox; ray.oy = hoy; ray.oz = hoz; ray.idx = hix; ray.idy = hiy; ray.idz = hiz;
+                    ray.octinv = hoct; ray.magic = p.byte_magic;
+                    r = ~(int64_t)hcol;
+                    tmax = p.tmax;
+                    if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[hcol] >> 32));
+                    trav_init(tv);
+                    tv.gx = sgx; tv.gy = sgy;
+                    ty = 0u;
+                    nodes_done = false; active = true;
+                }
             }
         }
 
@@ -351,10 +415,18 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
             while (ty != 0u && pos < kPairCap) {
                 const int b = ffs32(ty) - 1;
                 ty &= ty - 1u;
-                s_pair[warp][pos] = make_uint2(tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b)), (uint32_t)lane);
+                s_pair[warp][pos] = make_uint2(tx + (uint32_t)popc32(tmask & ~(0xffffffffu << b)), (uint32_t)(DRAIN ? owner_col() & 31 : lane));
                 ++pos;
             }
             n_pend = n_pend + total < kPairCap ? n_pend + total : kPairCap;
+        }
+        return 0;
+    };
+    int rc;
+    do { rc = step(std::false_type{}); } while (rc == 0);
+    if constexpr (kShare) {
+        if (rc == 2) {
+            while (step(std::true_type{}) == 0) {}
         }
     }
     if (MODE == kContains) {

@@ -57,6 +57,7 @@ class TraceOpts(C.Structure):
 SCHED_AUTO, SCHED_DIRECT, SCHED_QUEUED, SCHED_COOP_COHERENT, SCHED_COOP_INCOHERENT, SCHED_SLOTS = 0, 1, 2, 3, 4, 5
 OPT_SCRATCH_ZEROED = 1
 OPT_STOP_WHEN_BROKEN = 2
+OPT_NO_LANE_SHARING = 4
 
 
 class Pinhole(C.Structure):
@@ -174,11 +175,12 @@ def _env_int(name: str) -> int:
 # Scheduling knobs for experiments (tools/), read ONCE at import; 0 = the library's defaults.  The C library itself
 # reads no environment variable on the trace path: everything a launch depends on is in rt_trace_opts.
 _KNOBS = dict(schedule=_env_int("TRIRO_SCHED"), refill_threshold=_env_int("TRIRO_REFILL_THRESHOLD"),
-              tri_threshold=_env_int("TRIRO_TRI_THRESHOLD"), grid_div=_env_int("TRIRO_GRID_DIV"))
+              tri_threshold=_env_int("TRIRO_TRI_THRESHOLD"), grid_div=_env_int("TRIRO_GRID_DIV"),
+              no_lane_sharing=_env_int("TRIRO_NO_LANE_SHARING"))
 
 
 def set_knobs(**kw) -> dict:
-    """Override the experiment knobs (schedule, refill_threshold, tri_threshold, grid_div) for later calls of this
+    """Override the experiment knobs (schedule, refill_threshold, tri_threshold, grid_div, no_lane_sharing) for later calls of this
     process; returns the previous values.  Every schedule gives bit-identical results."""
     old = dict(_KNOBS)
     for k, v in kw.items():
@@ -196,7 +198,7 @@ def trace_opts(accel=None, ray_first: int = 0, ray_count: int = -1, scratch_zero
     and the experiment knobs.  The whole-batch form is cached per (tmax, knobs)."""
     if ray_first == 0 and ray_count < 0 and scratch_zeroed:
         tm = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
-        key = (tm, _KNOBS["schedule"], _KNOBS["refill_threshold"], _KNOBS["tri_threshold"], _KNOBS["grid_div"])
+        key = (tm, *_KNOBS.values())
         o = _opts_cache.get(key)
         if o is None:
             o = _opts_cache[key] = _trace_opts(accel, 0, -1, True)
@@ -209,7 +211,7 @@ def _trace_opts(accel, ray_first: int, ray_count: int, scratch_zeroed: bool) -> 
     o.tmax = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
     o.schedule = _KNOBS["schedule"]
     o.ray_first, o.ray_count = int(ray_first), max(int(ray_count), 0)     # 0 = up to the end of the batch
-    o.flags = OPT_SCRATCH_ZEROED if scratch_zeroed else 0
+    o.flags = (OPT_SCRATCH_ZEROED if scratch_zeroed else 0) | (OPT_NO_LANE_SHARING if _KNOBS["no_lane_sharing"] else 0)
     o.refill_threshold, o.tri_threshold, o.grid_div = _KNOBS["refill_threshold"], _KNOBS["tri_threshold"], _KNOBS["grid_div"]
     return o
 
