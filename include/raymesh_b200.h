@@ -128,6 +128,9 @@ typedef struct rt_blob_header {
 #define RT_OPT_NO_LANE_SHARING 4u  /* cooperative schedules: lanes of a warp that can draw no more rays normally take over
                                       part of a neighbour's traversal stack (results are identical either way); this
                                       switches that off (experiments) */
+#define RT_OPT_NO_TILE_ORDER 8u    /* coherent image batches [.., H, W, 3] (H % 4 == 0, W % 8 == 0) are normally traced in
+                                      8x4-pixel tiles per warp instead of 32-pixel row segments (same results, indexed
+                                      by ray); this keeps the row order (experiments) */
 typedef struct rt_trace_opts {
     float tmax;
     int32_t schedule;

@@ -111,6 +111,43 @@ def test_lane_sharing_in_the_launch_tail_changes_no_bit(cuda_device, n_rays):
     check_closest_vs_mirror(res[0]["closest"], om, flat(o), flat(d))
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (4, 8), (36, 40), (30, 64), (64, 36), (3, 32, 64), (1, 2048)])
+def test_tile_work_order_of_image_batches_changes_no_bit(cuda_device, shape):
+    """Coherent image batches [H, W, 3] with H % 4 == 0 and W % 8 == 0 are traced in 8x4-pixel tiles per warp (rt_trace.cu
+    tile_order); other shapes and batches of several images keep the row order.  Results are indexed by ray: tile order
+    on / off (RT_OPT_NO_TILE_ORDER) and the oracle must agree on every bit, whatever the shape."""
+    v, f = synth.icosphere(4)
+    g = torch.Generator().manual_seed(21)
+    d = torch.randn((*shape, 3), generator=g)
+    d[..., 2] = -d[..., 2].abs() - 0.3
+    d = d.to(cuda_device)
+    o = torch.tensor([0.05, -0.02, 3.0], device=cuda_device).broadcast_to(d.shape)
+    r = make(v, f)
+    res = []
+    for kw in (dict(), dict(no_tile_order=1), dict(schedule=hops.SCHED_DIRECT)):
+        with knobs(**kw):
+            got = dict(closest=closest_to_numpy(r.intersects_closest(o, d)), first=r.intersects_first(o, d).cpu().numpy(),
+                       any=r.intersects_any(o, d).cpu().numpy(), count=r.intersects_count(o, d).cpu().numpy())
+            h6 = r.intersects_closest(o, d, stream_compaction=True)
+            got["compact"] = tuple(x.cpu().numpy() for x in h6)
+            loc, ray_idx, tri_idx = r.intersects_location(o, d)
+            key = np.lexsort((tri_idx.cpu().numpy(), ray_idx.cpu().numpy()))
+            got["location"] = (ray_idx.cpu().numpy()[key], tri_idx.cpu().numpy()[key], loc.cpu().numpy()[key])
+        res.append(got)
+    assert res[0]["count"].shape == tuple(shape)
+    for got in res[1:]:
+        for k in got["closest"]:
+            assert_bits_equal(got["closest"][k], res[0]["closest"][k], f"closest.{k}")
+        for k in ("first", "any", "count"):
+            assert np.array_equal(got[k], res[0][k]), k
+        for a, b_ in zip(got["compact"], res[0]["compact"]):
+            assert_bits_equal(a, b_, "compact")
+        for a, b_ in zip(got["location"], res[0]["location"]):
+            assert_bits_equal(a, b_, "location")
+    om = oracle.OracleMesh(v, f)
+    check_closest_vs_mirror(res[0]["closest"], om, flat(o), flat(d))
+
+
 def test_trace_stats_direct_equals_host_simulation_and_coop_never_skips(cuda_device):
     v, f = synth.icosphere(4)
     r = make(v, f)

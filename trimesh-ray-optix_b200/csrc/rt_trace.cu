@@ -55,6 +55,8 @@ struct TraceParams {
     const uint8_t* active;       // optional per-point mask (may alias `broken`)
     int stop_on_broken;          // RT_OPT_STOP_WHEN_BROKEN
     int share_lanes;             // !RT_OPT_NO_LANE_SHARING
+    // coherent image batches [.., H, W, 3]: work index -> ray index by 8x4-pixel tiles (0 = identity), see tile_order()
+    uint32_t tile_per_row, tile_w, tile_hw;
     uint8_t* contain;
     uint8_t* broken;
     int32_t* flags;
@@ -77,6 +79,20 @@ struct LocalStack {
 struct TraceParams;
 __device__ __forceinline__ void release_scratch(const TraceParams& p);
 
+// Work order of coherent image batches.  Lanes draw consecutive WORK indices; with the identity a warp holds 32
+// consecutive pixels of one row.  For a batch shaped [.., H, W, 3] with H % 4 == 0 and W % 8 == 0 the work index is
+// mapped to the ray index so that 32 consecutive work items are an 8x4-pixel tile: the rays of a warp then visit
+// fewer distinct leaf-level nodes per step (fewer L1 lines per request), and a warp on the silhouette of an object
+// mixes grazing rays with short ones (idle lanes for lane sharing).  Results are indexed by ray, so nothing else changes.
+#ifndef RT_TILE_FRAMES
+#define RT_TILE_FRAMES 0
+#endif
+#ifndef RT_TILE_INLINE
+#define RT_TILE_INLINE __forceinline__
+#endif
+struct TraceParams;
+__device__ RT_TILE_INLINE int64_t tile_order(const TraceParams& p, int64_t w);
+
 enum FetchMode { kGeneral = 0, kPacked = 1, kConstant = 2, kGeneral32 = 3, kPinhole = 4 };
 
 __device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int64_t stride[4], int mode, int64_t r) {
@@ -98,6 +114,25 @@ __device__ __forceinline__ int64_t ray_offset(const int64_t shape[4], const int6
 // Origin and direction of ray r: strided fetch (reference getRay, shaders.cu:35-63), the fixed direction
 // of contains_points, or a pinhole camera ray generated in registers (reference gen_rays,
 // test/performance_test.py:10-20: d = normalize(x - (w-1)/2, y - (h-1)/2, -f) @ cam_mat^T).
+__device__ RT_TILE_INLINE int64_t tile_order(const TraceParams& p, int64_t w) {
+    if (p.tile_per_row == 0u) return w;
+#if RT_TILE_FRAMES
+    uint32_t frame = 0u;
+    if ((uint64_t)w >= (uint64_t)p.tile_hw) frame = (uint32_t)((uint64_t)w / p.tile_hw);     // batches of several images
+    const uint32_t t = (uint32_t)(w - (int64_t)frame * p.tile_hw);
+#else
+    const uint32_t t = (uint32_t)w;                         // one image (launch() enables tiles for those only)
+#endif
+    const uint32_t tile = t >> 5, j = t & 31u;
+    const uint32_t trow = tile / p.tile_per_row, tcol = tile - trow * p.tile_per_row;
+    const uint32_t q = (trow * 4u + (j >> 3)) * p.tile_w + tcol * 8u + (j & 7u);
+#if RT_TILE_FRAMES
+    return (int64_t)frame * p.tile_hw + (int64_t)q;
+#else
+    return (int64_t)q;
+#endif
+}
+
 template <int MODE>
 __device__ __forceinline__ void load_ray(const TraceParams& p, int64_t r_local, float& ox, float& oy, float& oz, float& dx,
                                          float& dy, float& dz) {
@@ -598,6 +633,13 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     // Anything else is treated as incoherent: rays prepared 32 at a time into a pool, early re-fill.  Both use
     // the warp-cooperative triangle tests of rt_trace_coop.cuh.
     const bool coherent = MODE != kContains && (p.o_mode == kConstant || pinhole);
+    p.tile_per_row = 0u;
+    if (coherent && !(o.flags & RT_OPT_NO_TILE_ORDER) && o.ray_first == 0 && count == rays->nray) {
+        const int64_t h = rays->shape[1], w = rays->shape[2];
+        if (h > 0 && w > 0 && h % 4 == 0 && w % 8 == 0 && h * w < ((int64_t)1 << 31) && (RT_TILE_FRAMES ? rays->nray < ((int64_t)1 << 40) : rays->nray == h * w)) {
+            p.tile_per_row = (uint32_t)(w / 8); p.tile_w = (uint32_t)w; p.tile_hw = (uint32_t)(h * w);
+        }
+    }
     int sched = o.schedule;
     RT_REQUIRE(sched >= RT_SCHED_AUTO && sched <= RT_SCHED_SLOTS, RT_ERR_INVALID, "%s: unknown schedule %d", fn, sched);
     if (sched == RT_SCHED_AUTO) sched = coherent ? RT_SCHED_COOP_COHERENT : RT_SCHED_COOP_INCOHERENT;

@@ -316,6 +316,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     if (!active) {
                         r = (int64_t)base + __popc(idle & lt_mask);
                         bool take = r < nray;
+                        if (take) r = tile_order(p, r);
                         if constexpr (MODE == kContains) { if (take && p.active && !p.active[r]) take = false; }
                         if (take) {
                             float ox, oy, oz, dx, dy, dz;

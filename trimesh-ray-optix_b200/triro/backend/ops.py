@@ -58,6 +58,7 @@ SCHED_AUTO, SCHED_DIRECT, SCHED_QUEUED, SCHED_COOP_COHERENT, SCHED_COOP_INCOHERE
 OPT_SCRATCH_ZEROED = 1
 OPT_STOP_WHEN_BROKEN = 2
 OPT_NO_LANE_SHARING = 4
+OPT_NO_TILE_ORDER = 8
 
 
 class Pinhole(C.Structure):
@@ -176,11 +177,11 @@ def _env_int(name: str) -> int:
 # reads no environment variable on the trace path: everything a launch depends on is in rt_trace_opts.
 _KNOBS = dict(schedule=_env_int("TRIRO_SCHED"), refill_threshold=_env_int("TRIRO_REFILL_THRESHOLD"),
               tri_threshold=_env_int("TRIRO_TRI_THRESHOLD"), grid_div=_env_int("TRIRO_GRID_DIV"),
-              no_lane_sharing=_env_int("TRIRO_NO_LANE_SHARING"))
+              no_lane_sharing=_env_int("TRIRO_NO_LANE_SHARING"), no_tile_order=_env_int("TRIRO_NO_TILE_ORDER"))
 
 
 def set_knobs(**kw) -> dict:
-    """Override the experiment knobs (schedule, refill_threshold, tri_threshold, grid_div, no_lane_sharing) for later calls of this
+    """Override the experiment knobs (schedule, refill_threshold, tri_threshold, grid_div, no_lane_sharing, no_tile_order) for later calls of this
     process; returns the previous values.  Every schedule gives bit-identical results."""
     old = dict(_KNOBS)
     for k, v in kw.items():
@@ -211,7 +212,7 @@ def _trace_opts(accel, ray_first: int, ray_count: int, scratch_zeroed: bool) -> 
     o.tmax = float(getattr(getattr(accel, "_inner", accel), "tmax", TMAX_DEFAULT)) if accel is not None else TMAX_DEFAULT
     o.schedule = _KNOBS["schedule"]
     o.ray_first, o.ray_count = int(ray_first), max(int(ray_count), 0)     # 0 = up to the end of the batch
-    o.flags = (OPT_SCRATCH_ZEROED if scratch_zeroed else 0) | (OPT_NO_LANE_SHARING if _KNOBS["no_lane_sharing"] else 0)
+    o.flags = (OPT_SCRATCH_ZEROED if scratch_zeroed else 0) | (OPT_NO_LANE_SHARING if _KNOBS["no_lane_sharing"] else 0) | (OPT_NO_TILE_ORDER if _KNOBS["no_tile_order"] else 0)
     o.refill_threshold, o.tri_threshold, o.grid_div = _KNOBS["refill_threshold"], _KNOBS["tri_threshold"], _KNOBS["grid_div"]
     return o
 
