@@ -148,6 +148,51 @@ def test_tile_work_order_of_image_batches_changes_no_bit(cuda_device, shape):
     check_closest_vs_mirror(res[0]["closest"], om, flat(o), flat(d))
 
 
+@pytest.mark.parametrize("mesh", ["cube", "flat_plane", "slab_heightfield", "far_offset_cube"])
+def test_root_frame_pretest_rejects_only_rays_that_hit_nothing(cuda_device, mesh):
+    """Pooled kernels test every ray against the box that bounds the root's children before it may take a lane, and
+    write the miss of a rejected ray at once (rt_trace_coop.cuh fill_pool_frame / rt_core.cuh frame_missed).  Rays that
+    graze that box - along faces, through edges and corners, starting on it, inside a zero-thickness frame - must come
+    out exactly as the oracle's brute-force mirror says: closest hit, count and any."""
+    if mesh in ("cube", "far_offset_cube"):
+        c = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32)
+        f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5], [0, 4, 7], [0, 7, 3]], np.int32)
+        v = c + (np.array([1000.25, -2000.5, 3000.125], np.float32) if mesh == "far_offset_cube" else 0)
+    elif mesh == "flat_plane":
+        v, f = synth.heightfield(8, 8)
+        v = v.copy(); v[:, 2] = 0.25                       # zero-thickness root frame
+    else:
+        v, f = synth.heightfield(64, 32)
+    lo, hi = v.min(0), v.max(0)
+    g = np.random.default_rng(31)
+    n = 40_000
+    o = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32)
+    # origins on / just off the bounding planes, directions along the axes, the face diagonals, towards corners, random
+    grid = np.stack([lo, (lo + hi) / 2, hi, lo - (hi - lo + 1) * 0.5, hi + (hi - lo + 1) * 0.5])      # 5 x 3 coordinates per axis
+    o[:] = grid[g.integers(0, 5, (n, 3)), np.arange(3)]
+    kind = g.integers(0, 4, n)
+    axes = np.eye(3, dtype=np.float32)[g.integers(0, 3, n)] * g.choice([-1.0, 1.0], (n, 1))
+    diag = g.choice([-1.0, 0.0, 1.0], (n, 3)).astype(np.float32)
+    diag[(diag == 0).all(1)] = [1, 0, 0]
+    corner = grid[g.integers(0, 3, (n, 3)), np.arange(3)] - o
+    corner[(corner == 0).all(1)] = [0, 0, 1]
+    rnd = g.normal(size=(n, 3)).astype(np.float32)
+    d[:] = np.where((kind == 0)[:, None], axes, np.where((kind == 1)[:, None], diag, np.where((kind == 2)[:, None], corner, rnd)))
+    jitter = g.integers(0, 3, n)                            # a third of the origins move by one ulp
+    o = np.where((jitter == 1)[:, None], np.nextafter(o, np.float32(np.inf)), np.where((jitter == 2)[:, None], np.nextafter(o, np.float32(-np.inf)), o)).astype(np.float32)
+    ot, dt = torch.from_numpy(o).to(cuda_device), torch.from_numpy(d.astype(np.float32)).to(cuda_device)
+    r = make(v, f)
+    om = oracle.OracleMesh(v, f, use_bvh=False)
+    got = closest_to_numpy(r.intersects_closest(ot, dt))
+    check_closest_vs_mirror(got, om, o, d.astype(np.float32))
+    ref = oracle.query(om, o, d.astype(np.float32), oracle.MIRROR, want=("count",))["count"]
+    assert np.array_equal(r.intersects_count(ot, dt).cpu().numpy(), ref), "count vs mirror"
+    assert np.array_equal(r.intersects_any(ot, dt).cpu().numpy(), ref > 0), "any vs mirror"
+    with knobs(schedule=hops.SCHED_DIRECT):                # the per-lane kernel has no pre-test
+        assert np.array_equal(r.intersects_count(ot, dt).cpu().numpy(), ref)
+    assert 0.02 < (ref > 0).mean() < 0.98
+
+
 def test_trace_stats_direct_equals_host_simulation_and_coop_never_skips(cuda_device):
     v, f = synth.icosphere(4)
     r = make(v, f)

@@ -124,6 +124,17 @@ struct Ray {
 };
 constexpr uint32_t kByteMagic = 0x47000000u;
 
+// 1/d with zero components replaced by +-tiny; returns octinv = 7 - octant (octant bit a = (d_a < 0)).
+RT_HD uint32_t ray_inverse(float dx, float dy, float dz, float& idx, float& idy, float& idz) {
+    const float tiny = 1e-20f;
+    const float sx = fabsf(dx) < tiny ? (signbit(dx) ? -tiny : tiny) : dx;
+    const float sy = fabsf(dy) < tiny ? (signbit(dy) ? -tiny : tiny) : dy;
+    const float sz = fabsf(dz) < tiny ? (signbit(dz) ? -tiny : tiny) : dz;
+    idx = 1.0f / sx; idy = 1.0f / sy; idz = 1.0f / sz;
+    const uint32_t oct = (sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u);
+    return 7u - oct;
+}
+
 RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox; r.oy = oy; r.oz = oz;
     // kz = dimension where |d| is maximal (first maximum in x,y,z order)
@@ -142,13 +153,7 @@ RT_HD void ray_setup(Ray& r, float ox, float oy, float oz, float dx, float dy, f
     r.okx = sel3(kx, ox, oy, oz);
     r.oky = sel3(ky, ox, oy, oz);
     r.okz = sel3(kz, ox, oy, oz);
-    const float tiny = 1e-20f;
-    const float sx = fabsf(dx) < tiny ? (signbit(dx) ? -tiny : tiny) : dx;
-    const float sy = fabsf(dy) < tiny ? (signbit(dy) ? -tiny : tiny) : dy;
-    const float sz = fabsf(dz) < tiny ? (signbit(dz) ? -tiny : tiny) : dz;
-    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
-    const uint32_t oct = (sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u);
-    r.octinv = 7u - oct;
+    r.octinv = ray_inverse(dx, dy, dz, r.idx, r.idy, r.idz);
     r.magic = kByteMagic;
     r.kzf = kz | (dkz > 0.0f ? 4 : 0);
 }
@@ -387,6 +392,52 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
     }
     const uint32_t hm8 = ~miss & 0xffu;
     return finish_masks(hm8, n0.w >> 24, n1.z, r.octinv);
+}
+
+// The box that bounds every child slot of a node, in the node's quantised frame: smallest lower and largest upper
+// plane byte per axis (empty slots are stored inverted, 255 / 0, and drop out), as the floats 32768 + q node_test feeds
+// into its FMAs.
+struct RootFrame { float px, py, pz, sx, sy, sz, lox, loy, loz, hix, hiy, hiz; };
+RT_HD uint32_t bytes_min(uint32_t a, uint32_t b) {
+    uint32_t m = 255u;
+    for (int i = 0; i < 4; ++i) { const uint32_t x = (a >> (8 * i)) & 0xffu, y = (b >> (8 * i)) & 0xffu; m = x < m ? x : m; m = y < m ? y : m; }
+    return m;
+}
+RT_HD uint32_t bytes_max(uint32_t a, uint32_t b) {
+    uint32_t m = 0u;
+    for (int i = 0; i < 4; ++i) { const uint32_t x = (a >> (8 * i)) & 0xffu, y = (b >> (8 * i)) & 0xffu; m = x > m ? x : m; m = y > m ? y : m; }
+    return m;
+}
+RT_HD RootFrame root_frame(const U4& n0, const U4& n2, const U4& n3, const U4& n4) {
+    RootFrame f;
+    f.px = as_float(n0.x); f.py = as_float(n0.y); f.pz = as_float(n0.z);
+    f.sx = as_float((n0.w & 0xffu) << 23); f.sy = as_float(((n0.w >> 8) & 0xffu) << 23); f.sz = as_float(((n0.w >> 16) & 0xffu) << 23);
+    f.lox = 32768.0f + (float)bytes_min(n2.x, n2.y); f.loy = 32768.0f + (float)bytes_min(n2.z, n2.w); f.loz = 32768.0f + (float)bytes_min(n3.x, n3.y);
+    f.hix = 32768.0f + (float)bytes_max(n3.z, n3.w); f.hiy = 32768.0f + (float)bytes_max(n4.x, n4.y); f.hiz = 32768.0f + (float)bytes_max(n4.z, n4.w);
+    return f;
+}
+
+// true: the ray misses that box under node_test's own arithmetic (same a, b, margins, plane FMAs and clamp).  fmaf
+// is monotone in the plane byte, so each slot's near plane is >= and its far plane <= the frame's: a ray rejected here is
+// rejected by every slot of the node.
+RT_HD bool frame_missed(float ox, float oy, float oz, float idx, float idy, float idz, const RootFrame& f, float tmax) {
+    const float ax = f.sx * idx, ay = f.sy * idy, az = f.sz * idz;
+    const float bx = (f.px - ox) * idx, by = (f.py - oy) * idy, bz = (f.pz - oz) * idz;
+    const float ku = 3.6e-7f;
+    const float kq = 256.0f * ku + 0.00390625f;
+    const float ex = fmaf(kq, fabsf(ax), ku * fabsf(bx));
+    const float ey = fmaf(kq, fabsf(ay), ku * fabsf(by));
+    const float ez = fmaf(kq, fabsf(az), ku * fabsf(bz));
+    const float cnx = fmaf(-32768.0f, ax, bx - ex), cfx = fmaf(-32768.0f, ax, bx + ex);
+    const float cny = fmaf(-32768.0f, ay, by - ey), cfy = fmaf(-32768.0f, ay, by + ey);
+    const float cnz = fmaf(-32768.0f, az, bz - ez), cfz = fmaf(-32768.0f, az, bz + ez);
+    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+    const float tnx = fmaf(negx ? f.hix : f.lox, ax, cnx), tfx = fmaf(negx ? f.lox : f.hix, ax, cfx);
+    const float tny = fmaf(negy ? f.hiy : f.loy, ay, cny), tfy = fmaf(negy ? f.loy : f.hiy, ay, cfy);
+    const float tnz = fmaf(negz ? f.hiz : f.loz, az, cnz), tfz = fmaf(negz ? f.loz : f.hiz, az, cfz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    return shift_in_sign(tf - tn, 0u) != 0u;
 }
 
 }  // namespace rt

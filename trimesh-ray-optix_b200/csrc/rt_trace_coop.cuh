@@ -34,6 +34,56 @@ namespace rt {
 #endif
 constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
 constexpr int kTailLanes = 4;          // <= this many lanes with node work: test listed pairs every step
+#ifndef RT_ROOT_AT_FILL
+#define RT_ROOT_AT_FILL 1
+#endif
+#ifndef RT_FILL_INLINE
+#define RT_FILL_INLINE __forceinline__
+#endif
+// Pool fill with the root-frame test (see the call site), out of line on purpose: inlined, its registers pushed ptxas
+// into spilling traversal state around every node step; as a call the live registers are saved here and nowhere else.
+template <int MODE>
+__device__ RT_FILL_INLINE unsigned fill_pool_frame(const TraceParams& p, int64_t base, int n, float (*s_pool)[kTraceThreads],
+                                                   const RootFrame& s_root, int col0, int lane) {
+    // the frame test needs the origin and 1/d only: it runs before the (register-hungry) rest of the set-up
+    bool live = false;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+    if (lane < n) {
+        load_ray<MODE>(p, base + lane, ox, oy, oz, dx, dy, dz);
+        float idx, idy, idz;
+        ray_inverse(dx, dy, dz, idx, idy, idz);
+        live = !frame_missed(ox, oy, oz, idx, idy, idz, s_root, p.tmax);
+        if (!live) {
+            const int64_t q = base + lane;
+            if constexpr (MODE == kClosest) {
+                if (p.hit) {      // miss: reference miss program shaders.cu:128-135
+                    p.hit[q] = 0; p.front[q] = 0; p.tri[q] = -1;
+                    p.loc[3 * q] = 0.f; p.loc[3 * q + 1] = 0.f; p.loc[3 * q + 2] = 0.f;
+                    p.uv[2 * q] = 0.f; p.uv[2 * q + 1] = 0.f;
+                }
+            } else if constexpr (MODE == kFirst) {
+                if (p.tri) p.tri[q] = -1;
+            } else if constexpr (MODE == kAny) {
+                if (p.hit) p.hit[q] = 0;
+            } else {
+                if (p.count) p.count[q] = 0;     // count, all hits
+            }
+        }
+    }
+    const unsigned alive = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        Ray t;
+        ray_setup(t, ox, oy, oz, dx, dy, dz);
+        const int col = col0 + __popc(alive & ((1u << lane) - 1u));
+        s_pool[0][col] = t.ox; s_pool[1][col] = t.oy; s_pool[2][col] = t.oz;
+        s_pool[3][col] = t.Sx; s_pool[4][col] = t.Sy; s_pool[5][col] = t.Sz;
+        s_pool[6][col] = t.okx; s_pool[7][col] = t.oky; s_pool[8][col] = t.okz;
+        s_pool[9][col] = t.idx; s_pool[10][col] = t.idy; s_pool[11][col] = t.idz;
+        s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8) | (lane << 20));
+    }
+    return alive;
+}
+
 #ifndef RT_SHARE_TAIL
 #define RT_SHARE_TAIL 1
 #endif
@@ -47,13 +97,27 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
     constexpr bool kKey = MODE == kClosest || MODE == kFirst;
     constexpr bool kShare = SHARE && RT_SHARE_TAIL;
     __shared__ float s_ray[kRayWords][kTraceThreads];
-    __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim
+    // Shared memory is L1 taken away (one 256 KB array per SM, carve-out steps 100 / 132 / 164 KB): the arrays below are
+    // sized so that 7 resident CTAs of the pooled closest-hit kernel stay under 132 KB and 8 CTAs of the others under
+    // 100 / 132 KB (1 KB per CTA is reserved by the system).
+    __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim  (closest: prim << 1 | front)
     __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
-    __shared__ float s_attr[MODE == kClosest ? 6 : 1][kTraceThreads];    // loc(3), uv(2), front
-    __shared__ unsigned long long s_rayidx[MODE == kAllHits ? kTraceThreads : 1];   // all hits: where the owner's records go
+    __shared__ float s_attr[MODE == kClosest ? 5 : 1][kTraceThreads];    // loc(3), uv(2)
+    // ray index of the column's ray (all hits: where the owner's records go).  Pooled kernels keep the lane's ray index
+    // here instead of in two registers: their loop sits at the 64-register edge, and one register more spilled a value
+    // around every node step (soup -10 %, an L1TEX-bound kernel); it is touched when a ray starts and retires only.
+    constexpr bool kRInSmem = POOL;
+    __shared__ long long s_rayidx[(MODE == kAllHits || kRInSmem) ? kTraceThreads : 1];
     __shared__ uint2 s_pair[kTraceThreads / 32][kPairCap];               // (triangle record, owner lane)
-    __shared__ float s_pool[POOL ? kPoolWords : 1][kTraceThreads];
-    init_mask_luts();
+    constexpr bool kRootFirst = POOL && MODE != kContains && RT_ROOT_AT_FILL;
+    __shared__ float s_pool[POOL ? kPoolWords : 1][POOL ? kTraceThreads : 1];
+    __shared__ RootFrame s_root;
+    __shared__ long long s_pool_base[POOL ? kTraceThreads / 32 : 1];     // ray index of the pool's first ray, per warp (not a register: the loop is at the 64-register edge)
+    if (kRootFirst && threadIdx.x == 0) {
+        const uint8_t* np = p.blob + reinterpret_cast<const rt_blob_header*>(p.blob)->nodes_offset;
+        s_root = root_frame(ldg128(np), ldg128(np + 32), ldg128(np + 48), ldg128(np + 64));
+    }
+    init_mask_luts();     // ends with __syncthreads()
     const rt_blob_header* hdr = reinterpret_cast<const rt_blob_header*>(p.blob);
     const uint8_t* tris = p.blob + hdr->tris_offset;
     const uint8_t* nodes = p.blob + hdr->nodes_offset;
@@ -69,18 +133,20 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
     Trav tv;
     Ray ray;                          // only o, 1/d, octinv, magic stay live across iterations
     float tmax = p.tmax;
-    int64_t r = -1;
+    int64_t r_reg = -1;
+    auto ray_index = [&]() -> int64_t { if constexpr (kRInSmem) return (int64_t)s_rayidx[mycol]; else return r_reg; };
+    auto set_ray_index = [&](int64_t v) { if constexpr (kRInSmem) s_rayidx[mycol] = (long long)v; else r_reg = v; };
+    set_ray_index(0);                 // a lane without a ray must not read as a helper (negative index, see owner_col)
     bool active = false, exhausted = false, nodes_done = true;
     int phase = 0;
     uint32_t count_plus = 0;
     int n_pend = 0;                   // pairs in the warp's list (warp-uniform)
     int my_pend = 0;                  // != 0: some of them belong to this lane's ray
     int pool_head = 0, pool_count = 0;
-    int64_t pool_base = 0;
     uint32_t ty = 0u, tx = 0u, tmask = 0u;      // triangles of this lane's last node step not yet listed
     // column of the ray this lane walks for: its own, or (work sharing, RT_SHARE_TAIL) a neighbour's - a helper keeps
     // ~column in r, which it does not need (no extra register in the loop)
-    auto owner_col = [&]() -> int { return r < 0 ? (int)(~r) : mycol; };
+    auto owner_col = [&]() -> int { const int64_t r = ray_index(); return r < 0 ? (int)(~r) : mycol; };
     trav_init(tv);
 
     // ---- test every listed pair with the whole warp
@@ -110,7 +176,11 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                 if (STATS) ++st_tris;
                 if (tri_test(t, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, h) && h.t > 0.0f) {
                     if constexpr (kKey) {
-                        key = ((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned long long)(uint32_t)a.w;
+                        // equal t resolves to the smaller primitive index; closest hit carries the front flag in bit 0
+                        // (one word of shared memory per ray less), primitive indices are < 2^31 (int32 outputs)
+                        uint32_t low = (uint32_t)a.w;
+                        if constexpr (MODE == kClosest) low = (low << 1) | (tri_front(t, h) ? 1u : 0u);
+                        key = ((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned long long)low;
                         if (key < s_best[col]) { atomicMin(&s_best[col], key); won = true; }
                     } else if constexpr (MODE == kAny) {
                         if (h.t < p.tmax) s_cnt[col] = 1u;
@@ -121,7 +191,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                             const uint32_t k = atomicAdd(&s_cnt[col], 1u);
                             if (k < (uint32_t)p.max_hits) {
                                 const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
-                                p.staging[(size_t)s_rayidx[col] * p.max_hits + k] =
+                                p.staging[(size_t)s_rayidx[col] * (size_t)p.max_hits + k] =
                                     make_uint4(a.w, __float_as_uint(at.lx), __float_as_uint(at.ly), __float_as_uint(at.lz));
                             }
                         }
@@ -136,13 +206,12 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
                     s_attr[0][col] = at.lx; s_attr[1][col] = at.ly; s_attr[2][col] = at.lz;
                     s_attr[3][col] = at.uv0; s_attr[4][col] = at.uv1;
-                    s_attr[5][col] = tri_front(t, h) ? 1.0f : 0.0f;
                 }
             }
         }
         __syncwarp();
         n_pend = 0; my_pend = 0;
-        const int oc = DRAIN ? owner_col() : mycol;
+        const int oc = (DRAIN && active) ? owner_col() : mycol;
         if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[oc] >> 32));
         if constexpr (MODE == kAny) { if (active && s_cnt[oc]) { nodes_done = true; ty = 0u; } }   // early exit
     };
@@ -153,7 +222,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         s_ray[3][mycol] = t.okx; s_ray[4][mycol] = t.oky; s_ray[5][mycol] = t.okz;
         s_ray[6][mycol] = __int_as_float(t.kzf);
         if constexpr (kKey) s_best[mycol] = key_init; else s_cnt[mycol] = 0u;
-        if constexpr (MODE == kAllHits) s_rayidx[mycol] = (unsigned long long)r;
+        if constexpr (MODE == kAllHits && !kRInSmem) s_rayidx[mycol] = (long long)r_reg;
         tmax = p.tmax;
         trav_init(tv);
         nodes_done = false;
@@ -193,11 +262,13 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                 // work sharing (below): a helper that has listed everything simply becomes idle; a ray retires once no
                 // helper still walks or holds unlisted triangles for it (the list itself is empty here: the flush above
                 // ran, because no lane has node work left)
-                if (retire && r < 0) { active = false; r = 0; retire = false; }
-                const unsigned helped = __reduce_or_sync(0xffffffffu, (active && r < 0) ? 1u << ((int)(~r) & 31) : 0u);
+                bool helper = active && ray_index() < 0;
+                if (retire && helper) { active = false; set_ray_index(0); retire = false; helper = false; }
+                const unsigned helped = __reduce_or_sync(0xffffffffu, helper ? 1u << ((int)(~ray_index()) & 31) : 0u);
                 if ((helped >> lane) & 1u) retire = false;
             }
             if (retire) {
+                const int64_t r = ray_index();
                 if constexpr (MODE == kClosest || MODE == kFirst) {
                     const unsigned long long best = s_best[mycol];
                     const bool hit = best != key_init;
@@ -207,8 +278,8 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     } else if (p.hit) {
                         // miss: reference miss program shaders.cu:128-135
                         p.hit[r] = hit ? 1 : 0;
-                        p.front[r] = hit ? (s_attr[5][mycol] != 0.0f ? 1 : 0) : 0;
-                        p.tri[r] = hit ? (int32_t)(uint32_t)best : -1;
+                        p.front[r] = hit ? (uint8_t)((uint32_t)best & 1u) : 0;
+                        p.tri[r] = hit ? (int32_t)((uint32_t)best >> 1) : -1;
                         p.loc[3 * r] = hit ? s_attr[0][mycol] : 0.f; p.loc[3 * r + 1] = hit ? s_attr[1][mycol] : 0.f;
                         p.loc[3 * r + 2] = hit ? s_attr[2][mycol] : 0.f;
                         p.uv[2 * r] = hit ? s_attr[3][mycol] : 0.f; p.uv[2 * r + 1] = hit ? s_attr[4][mycol] : 0.f;
@@ -265,6 +336,21 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                         if (n <= 32) exhausted = true;
                         if (n <= 0) break;
                         if (n > 32) n = 32;
+                        if constexpr (kRootFirst) {
+                            // Rays are tested here, with all 32 lanes busy, against the box that bounds the root's children
+                            // in the root's own quantised frame (frame_missed: the arithmetic of node_test, so a ray it
+                            // rejects is rejected by every child slot of the root as well).  Such a ray gets its miss
+                            // written on the spot (32 consecutive rays: coalesced) and never takes a lane; the others
+                            // enter the pool, compacted.  Heightfields with 74 % missing rays: +8...12 %.  Testing the
+                            // whole root node here was tried: its registers made ptxas keep the lanes' ray registers in
+                            // local memory across the loop (soup -14 %).
+                            const unsigned alive = fill_pool_frame<MODE>(p, (int64_t)base, (int)n, s_pool, s_root, col0, lane);
+                            if (STATS && lane == 0) { st_rays += (unsigned)n - __popc(alive); st_nodes += (unsigned)n - __popc(alive); }
+                            if (lane == 0) s_pool_base[warp] = (long long)base;
+                            __syncwarp();
+                            pool_head = 0; pool_count = __popc(alive);
+                            continue;
+                        }
                         if (lane < n) {
                             float ox, oy, oz, dx, dy, dz;
                             load_ray<MODE>(p, (int64_t)base + lane, ox, oy, oz, dx, dy, dz);
@@ -279,8 +365,9 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                             s_pool[9][col] = t.idx; s_pool[10][col] = t.idy; s_pool[11][col] = t.idz;
                             s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8) | (skip << 16));
                         }
+                        if (lane == 0) s_pool_base[warp] = (long long)base;
                         __syncwarp();
-                        pool_base = (int64_t)base; pool_head = 0; pool_count = (int)n;
+                        pool_head = 0; pool_count = (int)n;
                     }
                     const int n_idle = __popc(idle);
                     const int take = n_idle < pool_count ? n_idle : pool_count;
@@ -288,8 +375,8 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     if (!active && my < take) {
                         const int col = col0 + pool_head + my;
                         const int packed = __float_as_int(s_pool[12][col]);
-                        if (!(packed >> 16)) {
-                            r = pool_base + pool_head + my;
+                        if (kRootFirst || !(packed >> 16)) {
+                            set_ray_index((int64_t)s_pool_base[warp] + (kRootFirst ? ((packed >> 20) & 31) : pool_head + my));
                             Ray t;
                             ray.ox = s_pool[0][col]; ray.oy = s_pool[1][col]; ray.oz = s_pool[2][col];
                             t.Sx = s_pool[3][col]; t.Sy = s_pool[4][col]; t.Sz = s_pool[5][col];
@@ -314,10 +401,11 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     base = __shfl_sync(0xffffffffu, base, leader);
                     if ((int64_t)base + n_idle >= nray) exhausted = true;
                     if (!active) {
-                        r = (int64_t)base + __popc(idle & lt_mask);
+                        int64_t r = (int64_t)base + __popc(idle & lt_mask);
                         bool take = r < nray;
                         if (take) r = tile_order(p, r);
                         if constexpr (MODE == kContains) { if (take && p.active && !p.active[r]) take = false; }
+                        set_ray_index(r);
                         if (take) {
                             float ox, oy, oz, dx, dy, dz;
                             load_ray<MODE>(p, r, ox, oy, oz, dx, dy, dz);
@@ -343,7 +431,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
         //          an order-independent atomicMin, so results do not depend on who walked which subtree; only the owner
         //          retires the ray.  Cuts the tail of a launch: a silhouette ray's 60 node steps spread over the warp.
         if constexpr (DRAIN) {
-            if (active && r < 0 && nodes_done && ty == 0u) { active = false; r = 0; }      // helper finished
+            if (active && nodes_done && ty == 0u && ray_index() < 0) { active = false; set_ray_index(0); }      // helper finished
             const unsigned idle = __ballot_sync(0xffffffffu, !active);
             const unsigned rich = __ballot_sync(0xffffffffu, active && !nodes_done && tv.sp > 0);
             if (idle != 0u && rich != 0u) {
@@ -364,7 +452,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                 if (get) {
                     ray.ox = hox; ray.oy = hoy; ray.oz = hoz; ray.idx = hix; ray.idy = hiy; ray.idz = hiz;
                     ray.octinv = hoct; ray.magic = p.byte_magic;
-                    r = ~(int64_t)hcol;
+                    set_ray_index(~(int64_t)hcol);
                     tmax = p.tmax;
                     if constexpr (kKey) tmax = __uint_as_float((uint32_t)(s_best[hcol] >> 32));
                     trav_init(tv);
