@@ -34,6 +34,12 @@ namespace rt {
 #endif
 constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
 constexpr int kTailLanes = 4;          // <= this many lanes with node work: test listed pairs every step
+#ifndef RT_FRONT_IN_KEY
+#define RT_FRONT_IN_KEY 1
+#endif
+#ifndef RT_R_SMEM_CLOSEST
+#define RT_R_SMEM_CLOSEST 0
+#endif
 #ifndef RT_ROOT_AT_FILL
 #define RT_ROOT_AT_FILL 1
 #endif
@@ -102,11 +108,12 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
     // 100 / 132 KB (1 KB per CTA is reserved by the system).
     __shared__ unsigned long long s_best[kKey ? kTraceThreads : 1];      // (t bits << 32) | prim  (closest: prim << 1 | front)
     __shared__ uint32_t s_cnt[kKey ? 1 : kTraceThreads];                 // count / any flag
-    __shared__ float s_attr[MODE == kClosest ? 5 : 1][kTraceThreads];    // loc(3), uv(2)
-    // ray index of the column's ray (all hits: where the owner's records go).  Pooled kernels keep the lane's ray index
-    // here instead of in two registers: their loop sits at the 64-register edge, and one register more spilled a value
-    // around every node step (soup -10 %, an L1TEX-bound kernel); it is touched when a ray starts and retires only.
-    constexpr bool kRInSmem = POOL;
+    __shared__ float s_attr[MODE == kClosest ? (RT_FRONT_IN_KEY ? 5 : 6) : 1][kTraceThreads];    // loc(3), uv(2) [, front]
+    // ray index of the column's ray (all hits: where the owner's records go).  The pooled 64-register kernels keep the
+    // lane's ray index here instead of in two registers: their loop sits at the register edge, and a value spilled around
+    // every node step costs the L1TEX-bound soup 10 %; it is touched when a ray starts and retires only.  (The pooled
+    // closest-hit kernel has 72 registers and keeps it there: measured equal or better.)
+    constexpr bool kRInSmem = POOL && (RT_R_SMEM_CLOSEST || MODE != kClosest);
     __shared__ long long s_rayidx[(MODE == kAllHits || kRInSmem) ? kTraceThreads : 1];
     __shared__ uint2 s_pair[kTraceThreads / 32][kPairCap];               // (triangle record, owner lane)
     constexpr bool kRootFirst = POOL && MODE != kContains && RT_ROOT_AT_FILL;
@@ -179,7 +186,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                         // equal t resolves to the smaller primitive index; closest hit carries the front flag in bit 0
                         // (one word of shared memory per ray less), primitive indices are < 2^31 (int32 outputs)
                         uint32_t low = (uint32_t)a.w;
-                        if constexpr (MODE == kClosest) low = (low << 1) | (tri_front(t, h) ? 1u : 0u);
+                        if constexpr (MODE == kClosest && RT_FRONT_IN_KEY) low = (low << 1) | (tri_front(t, h) ? 1u : 0u);
                         key = ((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned long long)low;
                         if (key < s_best[col]) { atomicMin(&s_best[col], key); won = true; }
                     } else if constexpr (MODE == kAny) {
@@ -206,6 +213,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     const HitAttr at = tri_attr(h, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
                     s_attr[0][col] = at.lx; s_attr[1][col] = at.ly; s_attr[2][col] = at.lz;
                     s_attr[3][col] = at.uv0; s_attr[4][col] = at.uv1;
+                    if constexpr (!RT_FRONT_IN_KEY) s_attr[5][col] = tri_front(t, h) ? 1.0f : 0.0f;
                 }
             }
         }
@@ -278,8 +286,13 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     } else if (p.hit) {
                         // miss: reference miss program shaders.cu:128-135
                         p.hit[r] = hit ? 1 : 0;
-                        p.front[r] = hit ? (uint8_t)((uint32_t)best & 1u) : 0;
-                        p.tri[r] = hit ? (int32_t)((uint32_t)best >> 1) : -1;
+                        if constexpr (RT_FRONT_IN_KEY) {
+                            p.front[r] = hit ? (uint8_t)((uint32_t)best & 1u) : 0;
+                            p.tri[r] = hit ? (int32_t)((uint32_t)best >> 1) : -1;
+                        } else {
+                            p.front[r] = hit ? (s_attr[RT_FRONT_IN_KEY ? 0 : 5][mycol] != 0.0f ? 1 : 0) : 0;
+                            p.tri[r] = hit ? (int32_t)(uint32_t)best : -1;
+                        }
                         p.loc[3 * r] = hit ? s_attr[0][mycol] : 0.f; p.loc[3 * r + 1] = hit ? s_attr[1][mycol] : 0.f;
                         p.loc[3 * r + 2] = hit ? s_attr[2][mycol] : 0.f;
                         p.uv[2 * r] = hit ? s_attr[3][mycol] : 0.f; p.uv[2 * r + 1] = hit ? s_attr[4][mycol] : 0.f;
