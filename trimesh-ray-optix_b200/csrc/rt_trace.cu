@@ -198,7 +198,7 @@ struct VisitorOf {
 // `refill_threshold` lanes are still busy (defaults below; TRIRO_REFILL_THRESHOLD overrides).
 constexpr int kRefillThresholdQueued = 28;
 constexpr int kRefillThresholdSlots = 29;             // slot schedule: a lane adopts a prepared ray as soon as 4 lanes are idle
-constexpr int kRefillThresholdCoopIncoherent = 24;   // measured: 24 beats 28 by 1-2 % on the heightfields (profiles/r2_sweeps.md)
+constexpr int kRefillThresholdCoopIncoherent = 26;   // sweep r: heightfields best at 24-26, soup at 26-28 (profiles/r2_sweeps.md)
 constexpr int kRefillThresholdDirect = 8;
 // Postponed triangle tests: every lane owns a queue of pending triangle record indices in shared
 // memory (s_queue[entry][thread], conflict-free).  Node steps only enqueue; a warp runs a triangle
