@@ -316,22 +316,24 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     active = false;
                 } else if constexpr (MODE == kContains) {
                     // reference: ray_optix.py:238-267 — count along +dir, then along -dir; contain = inside the AABB and
-                    // both counts odd, broken = they disagree on "odd" and one of them is 0.  What the second walk has to
-                    // find out depends on the first count c+ (same outputs, less work: soup 27.7 -> ~21 ms per 10 M points):
+                    // both counts odd, broken = they disagree on "odd" and one of them is 0 (symmetric in the two counts:
+                    // which walk comes first is free, see the pool fill).  What the second walk has to find out depends
+                    // on the first count c+ (same outputs, less work):
                     //   c+ == 0      nothing: contain = 0, broken = 1 whatever c- is
                     //   c+ even > 0  only whether c- == 0: an any-hit walk (kContainsAnyBit in s_cnt ends it at the first hit)
                     //   c+ odd       the parity of c-: the full count
                     const uint32_t c = s_cnt[mycol] & ~kContainsAnyBit;
-                    if (phase == 0 && c != 0u) {
+                    if (!(phase & 1) && c != 0u) {
                         count_plus = c;
                         Ray t;
-                        ray_setup(t, ray.ox, ray.oy, ray.oz, -p.dir[0], -p.dir[1], -p.dir[2]);
+                        const float sg = (phase & 4) ? 1.0f : -1.0f;     // the second walk goes the other way
+                        ray_setup(t, ray.ox, ray.oy, ray.oz, sg * p.dir[0], sg * p.dir[1], sg * p.dir[2]);
                         ray.idx = t.idx; ray.idy = t.idy; ray.idz = t.idz; ray.octinv = t.octinv;
                         start_ray(t);
                         if (!(c & 1u)) s_cnt[mycol] = kContainsAnyBit;
-                        phase = 1;
+                        phase |= 1;
                     } else {
-                        if (phase == 0) count_plus = 0u;           // c+ == 0: c (= 0) stands in for c-
+                        if (!(phase & 1)) count_plus = 0u;         // first count 0: c (= 0) stands in for the second
                         const bool inside = ray.ox > p.aabb_lo[0] && ray.oy > p.aabb_lo[1] && ray.oz > p.aabb_lo[2] &&
                                             ray.ox < p.aabb_hi[0] && ray.oy < p.aabb_hi[1] && ray.oz < p.aabb_hi[2];
                         const bool agree = (count_plus & 1u) && (c & 1u);
@@ -376,16 +378,35 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                         if (lane < n) {
                             float ox, oy, oz, dx, dy, dz;
                             load_ray<MODE>(p, (int64_t)base + lane, ox, oy, oz, dx, dy, dz);
+                            int skip = 0, flip = 0;
+                            if constexpr (MODE == kContains) {
+                                if (p.active && !p.active[(int64_t)base + lane]) skip = 1;
+                                // contain / broken are symmetric in the two counts, so a point inside the AABB walks FIRST
+                                // towards the side where it leaves the AABB sooner: the short walk is cheap and most
+                                // likely to count 0, which settles the point without the long walk (see the retirement)
+                                float tp = 3.0e38f, tm = 3.0e38f;
+                                const float o3[3] = {ox, oy, oz};
+                                bool in = true;
+#pragma unroll
+                                for (int a = 0; a < 3; ++a) {
+                                    const float d = p.dir[a], lo = p.aabb_lo[a] - o3[a], hi = p.aabb_hi[a] - o3[a];
+                                    in = in && lo < 0.0f && hi > 0.0f;
+                                    if (d != 0.0f) {
+                                        const float inv = __frcp_rn(d);
+                                        tp = fminf(tp, (d > 0.0f ? hi : lo) * inv);
+                                        tm = fminf(tm, (d > 0.0f ? lo : hi) * -inv);
+                                    }
+                                }
+                                if (in && tm < tp) { flip = 1; dx = -dx; dy = -dy; dz = -dz; }
+                            }
                             Ray t;
                             ray_setup(t, ox, oy, oz, dx, dy, dz);
-                            int skip = 0;
-                            if constexpr (MODE == kContains) { if (p.active && !p.active[(int64_t)base + lane]) skip = 1; }
                             const int col = col0 + lane;
                             s_pool[0][col] = t.ox; s_pool[1][col] = t.oy; s_pool[2][col] = t.oz;
                             s_pool[3][col] = t.Sx; s_pool[4][col] = t.Sy; s_pool[5][col] = t.Sz;
                             s_pool[6][col] = t.okx; s_pool[7][col] = t.oky; s_pool[8][col] = t.okz;
                             s_pool[9][col] = t.idx; s_pool[10][col] = t.idy; s_pool[11][col] = t.idz;
-                            s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8) | (skip << 16));
+                            s_pool[12][col] = __int_as_float(t.kzf | (int)(t.octinv << 8) | (skip << 16) | (flip << 17));
                         }
                         if (lane == 0) s_pool_base[warp] = (long long)base;
                         __syncwarp();
@@ -397,7 +418,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                     if (!active && my < take) {
                         const int col = col0 + pool_head + my;
                         const int packed = __float_as_int(s_pool[12][col]);
-                        if (kRootFirst || !(packed >> 16)) {
+                        if (kRootFirst || !((packed >> 16) & 1)) {
                             set_ray_index((int64_t)s_pool_base[warp] + (kRootFirst ? ((packed >> 20) & 31) : pool_head + my));
                             Ray t;
                             ray.ox = s_pool[0][col]; ray.oy = s_pool[1][col]; ray.oz = s_pool[2][col];
@@ -406,7 +427,7 @@ k_trace_coop(const __grid_constant__ TraceParams p) {
                             ray.idx = s_pool[9][col]; ray.idy = s_pool[10][col]; ray.idz = s_pool[11][col];
                             t.kzf = packed & 0xff; ray.octinv = ((uint32_t)packed >> 8) & 0xffu;
                             ray.magic = p.byte_magic;
-                            phase = 0;
+                            phase = (MODE == kContains && ((packed >> 17) & 1)) ? 4 : 0;     // bit 2: the first walk goes along -dir
                             start_ray(t);
                         }
                     }
