@@ -111,7 +111,9 @@ typedef struct rt_blob_header {
  *   flags       RT_OPT_SCRATCH_ZEROED: the caller guarantees that `scratch` is all zero on entry
  *               (stream-ordered); the kernel then restores it to zero before it exits, so a launch
  *               is exactly one kernel and the same scratch can be reused by the next call on the
- *               same stream without a memset.  RT_OPT_STOP_WHEN_BROKEN: see below.
+ *               same stream without a memset.  RT_OPT_STOP_WHEN_BROKEN, RT_OPT_NO_LANE_SHARING,
+ *               RT_OPT_NO_TILE_ORDER: see below (the last two switch off scheduling refinements that never
+ *               change a result; they exist for A/B measurements and tests).
  */
 #define RT_SCHED_AUTO 0
 #define RT_SCHED_DIRECT 1       /* triangles tested inside the node step, per lane (round-1 coherent schedule) */
