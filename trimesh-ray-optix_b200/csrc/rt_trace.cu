@@ -84,6 +84,10 @@ __device__ __forceinline__ void release_scratch(const TraceParams& p);
 // mapped to the ray index so that 32 consecutive work items are an 8x4-pixel tile: the rays of a warp then visit
 // fewer distinct leaf-level nodes per step (fewer L1 lines per request), and a warp on the silhouette of an object
 // mixes grazing rays with short ones (idle lanes for lane sharing).  Results are indexed by ray, so nothing else changes.
+#ifndef RT_TILE_W_LOG2
+#define RT_TILE_W_LOG2 3
+#endif
+constexpr uint32_t kTileWLog2 = RT_TILE_W_LOG2, kTileW = 1u << kTileWLog2, kTileH = 32u >> kTileWLog2;   // 8 x 4 pixels per warp
 #ifndef RT_TILE_FRAMES
 #define RT_TILE_FRAMES 0
 #endif
@@ -125,7 +129,7 @@ __device__ RT_TILE_INLINE int64_t tile_order(const TraceParams& p, int64_t w) {
 #endif
     const uint32_t tile = t >> 5, j = t & 31u;
     const uint32_t trow = tile / p.tile_per_row, tcol = tile - trow * p.tile_per_row;
-    const uint32_t q = (trow * 4u + (j >> 3)) * p.tile_w + tcol * 8u + (j & 7u);
+    const uint32_t q = (trow * kTileH + (j >> kTileWLog2)) * p.tile_w + tcol * kTileW + (j & (kTileW - 1u));
 #if RT_TILE_FRAMES
     return (int64_t)frame * p.tile_hw + (int64_t)q;
 #else
@@ -636,8 +640,8 @@ static int launch(const char* fn, TraceParams& p, const void* blob, const rt_ray
     p.tile_per_row = 0u;
     if (coherent && !(o.flags & RT_OPT_NO_TILE_ORDER) && o.ray_first == 0 && count == rays->nray) {
         const int64_t h = rays->shape[1], w = rays->shape[2];
-        if (h > 0 && w > 0 && h % 4 == 0 && w % 8 == 0 && h * w < ((int64_t)1 << 31) && (RT_TILE_FRAMES ? rays->nray < ((int64_t)1 << 40) : rays->nray == h * w)) {
-            p.tile_per_row = (uint32_t)(w / 8); p.tile_w = (uint32_t)w; p.tile_hw = (uint32_t)(h * w);
+        if (h > 0 && w > 0 && h % kTileH == 0 && w % kTileW == 0 && h * w < ((int64_t)1 << 31) && (RT_TILE_FRAMES ? rays->nray < ((int64_t)1 << 40) : rays->nray == h * w)) {
+            p.tile_per_row = (uint32_t)(w / kTileW); p.tile_w = (uint32_t)w; p.tile_hw = (uint32_t)(h * w);
         }
     }
     int sched = o.schedule;
