@@ -34,6 +34,9 @@ if rank == 0:
 peer3 = sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=False)     # peer-to-peer copies instead
 if rank == 0:
     assert all(torch.equal(a, b) for a, b in zip(peer2, peer3))
+peer4 = sh.intersects_closest_to_root(o, d, root=0, outputs=outs, kernel_stores=False, chunks=3)   # windows, copies on a side stream
+if rank == 0:
+    assert all(torch.equal(a, b) for a, b in zip(peer2, peer4))
 assert (peer is None) == (rank != 0)
 # variable-length results packed on the root by the ranks' own scatter kernels
 comp_nccl = sh.intersects_closest(o, d, stream_compaction=True, gather=True)
