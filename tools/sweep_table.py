@@ -16,6 +16,7 @@ WHAT = {"a": "first cooperative kernel (k_trace_coop v1), 7 CTAs/SM", "a_mb8": "
         "q_nofill": "before the root-frame pre-test (-DRT_ROOT_AT_FILL=0), same box and run as q_fill",
         "q_fill": "root-frame pre-test at pool fill (default): rays that miss the box around the root's children never take a lane",
         "r_refill": "re-fill threshold of coop_incoherent with the root-frame test in place: heightfields 24-26, soup 26-28 -> default 26",
+        "s_pairs": "pair-list threshold of coop_incoherent with the root-frame test in place: 24 beats 16 by 1-2.5 % on the heightfields, 0.5 % on the soup -> default 24",
         "o_refill": "re-fill threshold of coop_incoherent, final kernels: the soup prefers 28-30, the heightfield 24-26, all within 2 % (default stays 24)"}
 print("# Round-2 schedule sweeps (one B200, CUDA events, L2 flushed, min of 5)\n")
 print("Scenes: config2 = 327 680-tri icosphere x 3840x2160 camera; ico8 = 1.31 M-tri icosphere, same camera; hf4m = 4.19 M-tri heightfield x 20 M random rays;")

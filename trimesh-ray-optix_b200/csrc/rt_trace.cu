@@ -215,7 +215,7 @@ constexpr int kQueueHigh = kQueueCap - kNodeMaxTris;   // 8: above this a lane m
 constexpr int kTriThreshold = 8;
 // warp-cooperative schedules (rt_trace_coop.cuh): pairs listed before the warp tests them
 constexpr int kPairThresholdCoherent = 16;
-constexpr int kPairThresholdIncoherent = 16;
+constexpr int kPairThresholdIncoherent = 24;
 constexpr int kPoolWords = 13;   // prepared ray: o, S, o permuted, 1/d, packed (kzf | octinv << 8)
 
 struct LaneQueue {
