@@ -33,7 +33,10 @@ namespace rt {
 #define RT_PAIR_CAP 128
 #endif
 constexpr int kPairCap = RT_PAIR_CAP;  // pairs a warp can list before it must test them
-constexpr int kTailLanes = 4;          // <= this many lanes with node work: test listed pairs every step
+#ifndef RT_TAIL_LANES
+#define RT_TAIL_LANES 4
+#endif
+constexpr int kTailLanes = RT_TAIL_LANES;          // <= this many lanes with node work: test listed pairs every step
 #ifndef RT_FRONT_IN_KEY
 #define RT_FRONT_IN_KEY 1
 #endif
