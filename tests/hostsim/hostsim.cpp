@@ -365,6 +365,33 @@ struct Checker {
 };
 }  // namespace
 
+// The root-frame test of the pooled kernels' fill (rt_core.cuh frame_missed) against the full root node test, ray by ray:
+// out[0] = rays the frame rejects, out[1] = of those, rays for which node_test still reports a hit slot (must be 0),
+// out[2] = rays the root node test rejects (>= out[0]).  Same code as the device runs (RT_HD).
+extern "C" int hs_frame_check(const uint8_t* blob, int64_t nray, const float* o, const float* d, uint64_t* out) {
+    const rt_blob_header* h = reinterpret_cast<const rt_blob_header*>(blob);
+    if (h->magic != RT_BLOB_MAGIC) return -4;
+    const uint8_t* np = blob + h->nodes_offset;
+    const U4 n0 = ldg128(np), n1 = ldg128(np + 16), n2 = ldg128(np + 32), n3 = ldg128(np + 48), n4 = ldg128(np + 64);
+    const RootFrame f = root_frame(n0, n2, n3, n4);
+    out[0] = out[1] = out[2] = 0;
+    for (int64_t r = 0; r < nray; ++r) {
+        Ray ray;
+        ray_setup(ray, o[3 * r], o[3 * r + 1], o[3 * r + 2], d[3 * r], d[3 * r + 1], d[3 * r + 2]);
+        float idx, idy, idz;
+        ray_inverse(d[3 * r], d[3 * r + 1], d[3 * r + 2], idx, idy, idz);
+        if (idx != ray.idx || idy != ray.idy || idz != ray.idz) return -5;      // the fill and the set-up must agree bit for bit
+        const bool rejected = frame_missed(ray.ox, ray.oy, ray.oz, idx, idy, idz, f, RT_TMAX_DEFAULT);
+        const uint32_t hm = node_test(ray, n0, n1, n2, n3, n4, 0.0f, RT_TMAX_DEFAULT);
+        out[0] += rejected; out[1] += rejected && hm != 0u; out[2] += hm == 0u;
+    }
+    return 0;
+}
+
+extern "C" void hs_tile_map(uint32_t n, uint32_t tiles_per_row, uint32_t width, uint32_t w_log2, uint32_t* out) {
+    for (uint32_t t = 0; t < n; ++t) out[t] = tile_map(t, tiles_per_row, width, w_log2);
+}
+
 extern "C" int hs_check_blob(const uint8_t* blob, size_t blob_bytes, uint64_t* info) {
     if (blob_bytes < RT_BLOB_HEADER_BYTES) return 100;
     rt_blob_header h; memcpy(&h, blob, sizeof(h));

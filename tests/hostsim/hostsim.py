@@ -37,6 +37,7 @@ def lib():
         _LIB.hs_build_sah.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t]
         _LIB.hs_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 10
         _LIB.hs_check_blob.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        _LIB.hs_frame_check.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.hs_blob_prims.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.hs_refit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t]
     return _LIB
@@ -89,6 +90,25 @@ def blob_prims(blob: np.ndarray, n_tris: int) -> np.ndarray:
     out = np.zeros(n_tris, dtype=np.int32)
     lib().hs_blob_prims(_p(np.ascontiguousarray(blob)), _p(out))
     return out
+
+
+def tile_map(height: int, width: int, w_log2: int = 3) -> np.ndarray:
+    """rt_core.cuh tile_map for every work index of a height x width image (the device's work order of image batches)."""
+    out = np.zeros(height * width, np.uint32)
+    lib().hs_tile_map(C.c_uint32(height * width), C.c_uint32(width >> w_log2), C.c_uint32(width), C.c_uint32(w_log2), _p(out))
+    return out
+
+
+def frame_check(blob: np.ndarray, origins, directions):
+    """(rays rejected by the root-frame test, rejected rays the root node test would still enter [must be 0],
+    rays the root node test rejects) - rt_core.cuh frame_missed vs node_test on the root, the code the device runs."""
+    o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros(3, np.uint64)
+    rc = lib().hs_frame_check(_p(blob), len(o), _p(o), _p(d), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"hs_frame_check failed: {rc}")
+    return int(out[0]), int(out[1]), int(out[2])
 
 
 def trace(blob: np.ndarray, mode: str, origins, directions):

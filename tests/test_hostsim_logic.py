@@ -203,3 +203,63 @@ def test_results_do_not_depend_on_the_bvh_topology(name):
     assert np.array_equal(ra["uv"].view(np.uint32), rb["uv"].view(np.uint32))
     assert np.array_equal(hostsim.trace(a, "count", o, d)["count"], hostsim.trace(b, "count", o, d)["count"])
     assert np.array_equal(hostsim.trace(a, "any", o, d)["hit"], hostsim.trace(b, "any", o, d)["hit"])
+
+
+@pytest.mark.parametrize("name", ["ico3", "cube", "flat", "hf", "soup", "far"])
+def test_root_frame_test_never_rejects_a_ray_the_root_node_test_enters(name):
+    """The pooled kernels drop a ray at pool fill when it misses the box around the root's child slots (rt_core.cuh
+    frame_missed).  That is only sound if such a ray fails EVERY slot of the root in node_test - checked here with the
+    very code the device runs (hostsim hs_frame_check), on random rays and on rays that graze the frame: along its faces,
+    through its edges and corners, starting on it, one ulp either side.  Also: the 1/d of the fill is the set-up's 1/d."""
+    g = np.random.default_rng(5)
+    if name == "ico3":
+        v, f = synth.icosphere(3)
+    elif name == "cube":
+        v = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32)
+        f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5], [0, 4, 7], [0, 7, 3]], np.int32)
+    elif name == "flat":
+        v, f = synth.heightfield(8, 8, amplitude=0.0)
+    elif name == "hf":
+        v, f = synth.heightfield(64, 32)
+    elif name == "soup":
+        v, f = synth.triangle_soup(5000, sigma=0.05, seed=3)
+    else:
+        v, f = synth.icosphere(2)
+        v = (v.astype(np.float64) * 3.0 + np.array([1000.25, -2000.5, 3000.125])).astype(np.float32)
+    blob = hostsim.build_blob(v, f)
+    lo, hi = v.min(0).astype(np.float64), v.max(0).astype(np.float64)
+    n = 60_000
+    ext = hi - lo + 1e-3
+    grid = np.stack([lo, (lo + hi) / 2, hi, lo - ext * 0.5, hi + ext * 0.5])
+    o = grid[g.integers(0, 5, (n, 3)), np.arange(3)].astype(np.float32)
+    kind = g.integers(0, 4, n)
+    axes = np.eye(3)[g.integers(0, 3, n)] * g.choice([-1.0, 1.0], (n, 1))
+    diag = g.choice([-1.0, 0.0, 1.0], (n, 3)); diag[(diag == 0).all(1)] = [1, 0, 0]
+    corner = grid[g.integers(0, 3, (n, 3)), np.arange(3)] - o; corner[(corner == 0).all(1)] = [0, 0, 1]
+    rnd = g.normal(size=(n, 3))
+    d = np.where((kind == 0)[:, None], axes, np.where((kind == 1)[:, None], diag, np.where((kind == 2)[:, None], corner, rnd))).astype(np.float32)
+    jit = g.integers(0, 3, n)
+    o = np.where((jit == 1)[:, None], np.nextafter(o, np.float32(np.inf)), np.where((jit == 2)[:, None], np.nextafter(o, np.float32(-np.inf)), o)).astype(np.float32)
+    rejected, unsound, root_rejects = hostsim.frame_check(blob, o, d)
+    assert unsound == 0
+    assert rejected <= root_rejects
+    assert rejected > n // 50                                  # the test does reject a good part of these rays
+    # plain random rays as well
+    ro, rd = synth.random_rays(20_000, seed=8, box=True)
+    ro = (ro.numpy().astype(np.float64) * (hi - lo).max() * 1.5 + (lo + hi) / 2).astype(np.float32)
+    r2, u2, _ = hostsim.frame_check(blob, ro, rd.numpy())
+    assert u2 == 0
+
+
+@pytest.mark.parametrize("h,w,w_log2", [(4, 8, 3), (360, 640, 3), (2160, 3840, 3), (8, 4, 2), (40, 36, 2), (2, 16, 4), (64, 96, 3)])
+def test_tile_work_order_is_a_bijection_made_of_tiles(h, w, w_log2):
+    """rt_core.cuh tile_map (the work order of coherent image batches): every pixel exactly once, and 32 consecutive
+    work items cover one tile of 2^w_log2 x (32 >> w_log2) pixels."""
+    m = hostsim.tile_map(h, w, w_log2).astype(np.int64)
+    assert np.array_equal(np.sort(m), np.arange(h * w))
+    tw, th = 1 << w_log2, 32 >> w_log2
+    y, x = m // w, m % w
+    for t in sorted({0, min(1, len(m) // 32 - 1), len(m) // 32 - 1}):
+        ys, xs = y[32 * t:32 * t + 32], x[32 * t:32 * t + 32]
+        assert ys.max() - ys.min() == th - 1 and xs.max() - xs.min() == tw - 1
+        assert ys.min() % th == 0 and xs.min() % tw == 0

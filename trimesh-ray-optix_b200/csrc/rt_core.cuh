@@ -394,6 +394,16 @@ RT_HD uint32_t node_test(const Ray& r, const U4& n0, const U4& n1, const U4& n2,
     return finish_masks(hm8, n0.w >> 24, n1.z, r.octinv);
 }
 
+// Work index -> pixel index of an image of width `width` (a multiple of the tile width) traced in tiles of
+// 2^w_log2 x (32 >> w_log2) pixels: 32 consecutive work items are one tile, tiles run row-major.  A bijection on
+// [0, H * width) when H is a multiple of the tile height (tests/test_hostsim_logic.py).
+RT_HD uint32_t tile_map(uint32_t t, uint32_t tiles_per_row, uint32_t width, uint32_t w_log2) {
+    const uint32_t tile_w = 1u << w_log2, tile_h = 32u >> w_log2;
+    const uint32_t tile = t >> 5, j = t & 31u;
+    const uint32_t trow = tile / tiles_per_row, tcol = tile - trow * tiles_per_row;
+    return (trow * tile_h + (j >> w_log2)) * width + tcol * tile_w + (j & (tile_w - 1u));
+}
+
 // The box that bounds every child slot of a node, in the node's quantised frame: smallest lower and largest upper
 // plane byte per axis (empty slots are stored inverted, 255 / 0, and drop out), as the floats 32768 + q node_test feeds
 // into its FMAs.

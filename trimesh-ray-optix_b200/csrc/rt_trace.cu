@@ -127,9 +127,7 @@ __device__ RT_TILE_INLINE int64_t tile_order(const TraceParams& p, int64_t w) {
 #else
     const uint32_t t = (uint32_t)w;                         // one image (launch() enables tiles for those only)
 #endif
-    const uint32_t tile = t >> 5, j = t & 31u;
-    const uint32_t trow = tile / p.tile_per_row, tcol = tile - trow * p.tile_per_row;
-    const uint32_t q = (trow * kTileH + (j >> kTileWLog2)) * p.tile_w + tcol * kTileW + (j & (kTileW - 1u));
+    const uint32_t q = tile_map(t, p.tile_per_row, p.tile_w, kTileWLog2);
 #if RT_TILE_FRAMES
     return (int64_t)frame * p.tile_hw + (int64_t)q;
 #else
