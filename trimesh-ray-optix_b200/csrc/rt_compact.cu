@@ -177,27 +177,35 @@ __global__ void __launch_bounds__(kScanThreads) k_compact_scatter(
     const uint8_t* __restrict__ front, const int32_t* __restrict__ tri, const float* __restrict__ loc,
     const float* __restrict__ uv, int64_t ray_base, uint8_t* __restrict__ front_out, RayIdx* __restrict__ ray_out,
     int32_t* __restrict__ tri_out, float* __restrict__ loc_out, float* __restrict__ uv_out) {
+    // The tile's hit rays are listed in shared memory in ray order (tile-local indices at their packed positions), then
+    // the whole CTA copies row k of the list with thread k: gathers from the dense arrays run over increasing, dense
+    // addresses and every store of the packed arrays is coalesced.  (Round 1 let each thread copy the hits of its own
+    // eight rays: strided 32-byte loads and scattered stores - 1.35 ms per 125 M rays against 0.8 ms of DRAM time.)
+    __shared__ uint16_t s_list[kScanTile];
     const int64_t tile = blockIdx.x;
-    const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    const int64_t t0 = tile * kScanTile;
+    const int64_t i0 = t0 + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
     load8(hit, i0, n, v);
     int sum = 0;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) sum += v[j];
     int tile_total;
-    const int excl = block_exclusive_scan(sum, &tile_total);
-    int64_t dst = tile_prefix[tile] + excl;
+    int k = block_exclusive_scan(sum, &tile_total);
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-        if (v[j]) {
-            const int64_t r = i0 + j;
-            front_out[dst] = front[r];
-            ray_out[dst] = (RayIdx)(ray_base + r);
-            tri_out[dst] = tri[r];
-            loc_out[3 * dst] = loc[3 * r]; loc_out[3 * dst + 1] = loc[3 * r + 1]; loc_out[3 * dst + 2] = loc[3 * r + 2];
-            uv_out[2 * dst] = uv[2 * r]; uv_out[2 * dst + 1] = uv[2 * r + 1];
-            ++dst;
-        }
+        if (v[j]) s_list[k++] = (uint16_t)(threadIdx.x * kScanItems + j);
+    }
+    __syncthreads();
+    const int64_t dst0 = tile_prefix[tile];
+    for (int q = threadIdx.x; q < tile_total; q += kScanThreads) {
+        const int64_t r = t0 + s_list[q];
+        const int64_t dst = dst0 + q;
+        front_out[dst] = front[r];
+        ray_out[dst] = (RayIdx)(ray_base + r);
+        tri_out[dst] = tri[r];
+        loc_out[3 * dst] = loc[3 * r]; loc_out[3 * dst + 1] = loc[3 * r + 1]; loc_out[3 * dst + 2] = loc[3 * r + 2];
+        uv_out[2 * dst] = uv[2 * r]; uv_out[2 * dst + 1] = uv[2 * r + 1];
     }
 }
 
