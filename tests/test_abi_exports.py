@@ -49,6 +49,27 @@ def test_struct_layouts_match_the_header():
     assert parsed["bad_index_faces"] == int.from_bytes(hdr[72:76], "little")
 
 
+def test_python_constants_match_the_header_defines():
+    """Schedules, option flags and the ABI version the ctypes host uses are the header's #defines."""
+    from triro.backend import ops
+
+    src = open(HEADER).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(RT_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+u?|\d+u?)\b", src)}
+    assert defs["RT_ABI_VERSION"] == ops.ABI_VERSION
+    for name in ("AUTO", "DIRECT", "QUEUED", "COOP_COHERENT", "COOP_INCOHERENT", "SLOTS"):
+        assert defs["RT_SCHED_" + name] == getattr(ops, "SCHED_" + name), name
+    for name in ("SCRATCH_ZEROED", "STOP_WHEN_BROKEN", "NO_LANE_SHARING", "NO_TILE_ORDER"):
+        assert defs["RT_OPT_" + name] == getattr(ops, "OPT_" + name), name
+    flags = [defs[k] for k in defs if k.startswith("RT_OPT_")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)      # distinct single bits
+    old = ops.set_knobs(no_lane_sharing=1, no_tile_order=1)
+    try:
+        assert ops.trace_opts().flags & (ops.OPT_NO_LANE_SHARING | ops.OPT_NO_TILE_ORDER) == ops.OPT_NO_LANE_SHARING | ops.OPT_NO_TILE_ORDER
+    finally:
+        ops.set_knobs(**old)
+    assert ops.trace_opts().flags & (ops.OPT_NO_LANE_SHARING | ops.OPT_NO_TILE_ORDER) == 0
+
+
 def test_size_queries_and_argument_validation(lib):
     ws, blob = C.c_size_t(), C.c_size_t()
     assert lib.rt_bvh_sizes(100, 200, C.byref(ws), C.byref(blob)) == 0
