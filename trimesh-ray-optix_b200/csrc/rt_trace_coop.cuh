@@ -11,13 +11,16 @@
 //     permuted origin, kz) lives in shared memory, column = lane, so any lane can read any ray
 //     without bank conflicts;
 //   * results merge through shared memory: closest hit is a 64-bit atomicMin on
-//     (float bits of t << 32 | primitive index) — t > 0, so the bit pattern orders like the value and
-//     equal t resolves to the smaller primitive index, exactly the rule of ClosestVisitor — count is a
+//     (float bits of t << 32 | primitive index << 1 | front flag) — t > 0, so the bit pattern orders like the
+//     value and equal t resolves to the smaller primitive index, exactly the rule of ClosestVisitor — count is a
 //     32-bit atomicAdd, any-hit a flag;
-//   * the lane whose pair wins computes location / uv / front right there, at the width of the pair
+//   * the lane whose pair wins computes location / uv right there, at the width of the pair
 //     batch, and parks them in shared memory; retiring a ray is then a plain copy (k_trace re-fetches
-//     and re-tests the winning triangle with the few lanes that retire together).
-//
+//     and re-tests the winning triangle with the few lanes that retire together);
+//   * pooled (incoherent) kernels test every ray against the box around the root's child slots while they prepare
+//     32 rays with all lanes busy; a ray that misses it has its miss written there and never takes a lane
+//     (fill_pool_frame below, rt_core.cuh frame_missed);
+//   * contains_points walks the second direction only as far as the first count leaves the answer open (retirement);
 //   * once a warp can draw no more rays (the tail of a launch; all of a small launch), lanes without a ray take
 //     over part of a busy neighbour's traversal stack (step 1b, template parameter SHARE): possible because
 //     everything a triangle test or a hit touches is addressed by the ray's shared-memory column, not by the lane.
@@ -49,8 +52,11 @@ constexpr int kTailLanes = RT_TAIL_LANES;          // <= this many lanes with no
 #ifndef RT_FILL_INLINE
 #define RT_FILL_INLINE __forceinline__
 #endif
-// Pool fill with the root-frame test (see the call site), out of line on purpose: inlined, its registers pushed ptxas
-// into spilling traversal state around every node step; as a call the live registers are saved here and nowhere else.
+// Pool fill with the root-frame test (see the call site).  The ORDER inside matters for the whole kernel: with the full
+// ray set-up before the frame test (or with the whole root node tested here) the register peak of this code made ptxas
+// keep traversal state in local memory around every node step (soup -9...-16 %); a __noinline__ call still left one such
+// spill.  Testing on (origin, 1/d) first and setting up only the survivors needs no spill at all (RT_FILL_INLINE is kept
+// for A/B builds).
 template <int MODE>
 __device__ RT_FILL_INLINE unsigned fill_pool_frame(const TraceParams& p, int64_t base, int n, float (*s_pool)[kTraceThreads],
                                                    const RootFrame& s_root, int col0, int lane) {
