@@ -146,3 +146,29 @@ def test_trace_opts_defaults_and_knobs_are_per_call():
     with pytest.raises(KeyError):
         ops.set_knobs(nonsense=1)
     assert ops.allhits_window_rays(8, 1 << 20) == (1 << 20) // 128 and ops.allhits_window_rays(64, 1) == 1024
+
+
+def test_contains_second_walk_shortcuts_preserve_the_reference_decisions():
+    """The fused contains kernel (rt_trace_coop.cuh, retirement of MODE == kContains) replaces the second count by what
+    the first count leaves open: nothing when it is 0, 'any hit?' when it is even, the full count when it is odd, and it
+    may take the two directions in either order.  Exhaustive check of that algebra against the reference's formulas
+    (triro/ray/ray_optix.py:262-267): contain = inside & odd(c+) & odd(c-), broken = ~(odd & odd) & (c+ == 0 | c- == 0)."""
+    def reference(cp, cm, inside):
+        agree = (cp & 1) and (cm & 1)
+        return bool(inside and agree), bool((not agree) and (cp == 0 or cm == 0))
+
+    def fused(first, second, inside):
+        if first == 0:
+            seen = 0                          # no second walk
+        elif first % 2 == 0:
+            seen = 1 if second > 0 else 0     # any-hit walk: stops at the first hit
+        else:
+            seen = second                     # full count
+        agree = (first & 1) and (seen & 1)
+        return bool(inside and agree), bool((not agree) and (first == 0 or seen == 0))
+
+    for cp in range(8):
+        for cm in range(8):
+            for inside in (False, True):
+                assert fused(cp, cm, inside) == reference(cp, cm, inside)
+                assert fused(cm, cp, inside) == reference(cp, cm, inside)      # nearer side first: either order
